@@ -1,0 +1,24 @@
+"""CPU oracle for the batched motion-imitation env step (TEST INFRASTRUCTURE ONLY).
+
+This package is a float64 NumPy restatement of the reference hot path
+(`OpenRoboRL/envs/quadruped_robot/...`).  It is the
+checker for the CUDA path: only `tests/`, `__graft_entry__.smoke()` and the
+`cpu_baseline` / `--impl reference` legs of `bench.py` may import it.  Nothing
+under `openroborl_b200/` imports it, and the product path has no CPU fallback.
+
+Pinning status
+--------------
+* Task logic (motion-file post-processing, frame lookup/interpolation, quaternion
+  helpers, Butterworth filter, PD motor model, reward terms, termination, target
+  observation, reset/RSI bookkeeping, observation pipeline): PINNED against the
+  reference's own, unmodified Python modules imported in the build container
+  (scripts/make_golden.py; fixtures under tests/golden/).  The third-party
+  `pybullet_utils.transformations` (pybullet==2.7.3, requirements.txt:5) is absent
+  from the container, so its published algorithm is restated in `oracle/xform.py`.
+* Rigid-body arithmetic that the reference delegates to PyBullet 2.7.3
+  (`stepSimulation`, `getLinkState`, contacts): PARITY UNPINNED.  PyBullet is not
+  installable here (no wheel, no network), so forward kinematics, the mass matrix,
+  inverse dynamics and the contact model are checked against an independent
+  textbook formulation (`oracle/rbd.py`: maximal-coordinate Jacobians on the raw
+  URDF tree) and by physical invariants, not against Bullet outputs.
+"""

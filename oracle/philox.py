@@ -1,0 +1,55 @@
+"""Philox4x32-10 counter-based generator (Salmon et al., SC'11), NumPy uint32/uint64.
+
+TEST INFRASTRUCTURE (see oracle/__init__.py).  The reference draws its reset randomness from the
+unseeded global `np.random` (imitation_task.py:1125-1141), so RNG-stream parity with it is
+impossible by construction.  The B200 env instead keys a counter-based
+generator by (seed, global robot id, episode index, draw index) so results do not depend on how
+robots are sharded; this file is the CPU statement of that contract.
+"""
+import numpy as np
+
+M0 = np.uint64(0xD2511F53)
+M1 = np.uint64(0xCD9E8D57)
+W0 = np.uint32(0x9E3779B9)
+W1 = np.uint32(0xBB67AE85)
+MASK = np.uint64(0xFFFFFFFF)
+
+
+def philox4x32(counter, key):
+    """counter (..., 4) uint32, key (..., 2) uint32 -> (..., 4) uint32."""
+    c = [np.asarray(counter[..., i], dtype=np.uint64) for i in range(4)]
+    k0 = np.asarray(key[..., 0], dtype=np.uint64)
+    k1 = np.asarray(key[..., 1], dtype=np.uint64)
+    for _ in range(10):
+        p0 = M0 * c[0]
+        p1 = M1 * c[2]
+        hi0, lo0 = p0 >> np.uint64(32), p0 & MASK
+        hi1, lo1 = p1 >> np.uint64(32), p1 & MASK
+        c = [(hi1 ^ c[1] ^ k0) & MASK, lo1, (hi0 ^ c[3] ^ k1) & MASK, lo0]
+        k0 = (k0 + np.uint64(W0)) & MASK
+        k1 = (k1 + np.uint64(W1)) & MASK
+    return np.stack([x.astype(np.uint32) for x in c], axis=-1)
+
+
+def u01_53(hi, lo):
+    """53-bit uniform in [0,1): ((hi << 21) | (lo >> 11)) * 2^-53."""
+    v = (np.asarray(hi, dtype=np.uint64) << np.uint64(21)) | (np.asarray(lo, dtype=np.uint64) >> np.uint64(11))
+    return v.astype(np.float64) * (1.0 / 9007199254740992.0)
+
+
+def reset_draws(seed, gid, episode, n_clips):
+    """The three draws of one episode reset (order of imitation_task.py:183, 701, 1107-1121).
+
+    Returns u_rsi in [0,1), clip id in [0, n_clips), u_time in [0,1).
+    """
+    gid = np.asarray(gid, dtype=np.uint32)
+    episode = np.asarray(episode, dtype=np.uint32)
+    key = np.stack([np.full(gid.shape, seed & 0xFFFFFFFF, dtype=np.uint32),
+                    np.full(gid.shape, (seed >> 32) & 0xFFFFFFFF, dtype=np.uint32)], axis=-1)
+    z = np.zeros_like(gid)
+    a = philox4x32(np.stack([gid, episode, z, z], axis=-1), key)
+    b = philox4x32(np.stack([gid, episode, z + np.uint32(1), z], axis=-1), key)
+    u_rsi = u01_53(a[..., 0], a[..., 1])
+    clip = ((a[..., 2].astype(np.uint64) * np.uint64(n_clips)) >> np.uint64(32)).astype(np.int64)
+    u_time = u01_53(b[..., 0], b[..., 1])
+    return u_rsi, clip, u_time
