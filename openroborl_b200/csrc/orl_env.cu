@@ -1,0 +1,488 @@
+// C ABI of the B200-native batched motion-imitation environment (include/orl.h).
+// Host side: handle management, motion-table preparation (double precision, restating
+// R/envs/quadruped_robot/task/motion_data.py:527-680), kernel launches.  No torch types, no exceptions
+// across the boundary.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "../../include/orl.h"
+#include "orl_kernels.cuh"
+
+struct orl_env {
+  orl_config cfg;
+  orl_robot_model model;
+  DevEnv dev;
+  int device;
+  bool motions_loaded;
+  int64_t launches;
+  std::string err;
+  // device allocations
+  float* d_state;
+  orl_robot_model* d_model;
+  double* d_stats;
+  std::vector<void*> d_motion;     // owned motion-table buffers
+  // host copies of the motion tables (tests / diagnostics)
+  std::vector<double> h_frames, h_vels, h_dur, h_dpos, h_dheading;
+  std::vector<int> h_nframes;
+  // pinned staging for the *_host entry points
+  float* p_act; float* p_obs; float* p_rew; uint8_t* p_done; uint8_t* p_mask;
+  float* d_act; float* d_obs; float* d_rew; uint8_t* d_done; uint8_t* d_mask;
+  cudaStream_t stream;
+};
+
+static int fail(orl_env* e, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (e) e->err = buf;
+  return code;
+}
+#define CUDA_TRY(e, call)                                                                              \
+  do {                                                                                                 \
+    cudaError_t _s = (call);                                                                           \
+    if (_s != cudaSuccess) return fail(e, ORL_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(_s)); \
+  } while (0)
+
+// ---- double-precision quaternion helpers (host) ------------------------------------------------------
+struct Qd { double x, y, z, w; };
+static Qd qd_mul(Qd a, Qd b) {
+  return Qd{a.x * b.w + a.y * b.z - a.z * b.y + a.w * b.x, -a.x * b.z + a.y * b.w + a.z * b.x + a.w * b.y,
+            a.x * b.y - a.y * b.x + a.z * b.w + a.w * b.z, -a.x * b.x - a.y * b.y - a.z * b.z + a.w * b.w};
+}
+static Qd qd_conj(Qd q) { return Qd{-q.x, -q.y, -q.z, q.w}; }
+static void qd_rot(Qd q, const double v[3], double out[3]) {
+  const double n2 = q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w;
+  Qd p{v[0], v[1], v[2], 0.0};
+  Qd qi{-q.x / n2, -q.y / n2, -q.z / n2, q.w / n2};
+  Qd r = qd_mul(qd_mul(q, p), qi);
+  out[0] = r.x; out[1] = r.y; out[2] = r.z;
+}
+static double qd_heading(Qd q) {   // pose3d.calc_heading
+  const double ex[3] = {1, 0, 0};
+  double r[3];
+  qd_rot(q, ex, r);
+  return atan2(r[1], r[0]);
+}
+static Qd qd_about_z(double angle) { return Qd{0, 0, sin(angle / 2), cos(angle / 2)}; }
+
+extern "C" int orl_abi_version(void) { return ORL_ABI_VERSION; }
+
+extern "C" const char* orl_last_error(const orl_env* env) { return env ? env->err.c_str() : "null handle"; }
+
+extern "C" int64_t orl_launch_count(const orl_env* env) { return env ? env->launches : 0; }
+
+static void fill_dev_cfg(orl_env* e) {
+  const orl_config& c = e->cfg;
+  DevCfg& d = e->dev.cfg;
+  d.n = c.num_robot; d.gid0 = c.gid0; d.seed = c.seed; d.action_repeat = c.action_repeat;
+  d.max_episode_steps = c.max_episode_steps; d.auto_reset = c.auto_reset; d.cycle_sync = c.enable_cycle_sync;
+  d.sim_dt = c.sim_time_step; d.env_dt = c.env_time_step; d.warmup_time = c.warmup_time; d.rsi_prob = c.ref_state_init_prob;
+  for (int i = 0; i < ORL_NUM_TAR_FRAMES; ++i) d.tar_steps[i] = c.tar_frame_steps[i];
+  d.w_pose = c.pose_weight; d.w_vel = c.velocity_weight; d.w_ee = c.end_effector_weight; d.w_root = c.root_pose_weight;
+  d.w_rootvel = c.root_velocity_weight;
+  d.s_pose = c.pose_err_scale; d.s_vel = c.velocity_err_scale; d.s_ee = c.end_effector_err_scale;
+  d.s_eeh = c.end_effector_height_err_scale; d.s_root = c.root_pose_err_scale; d.s_rootvel = c.root_velocity_err_scale;
+  d.dist_thr2 = c.dist_fail_threshold * c.dist_fail_threshold; d.rot_thr = c.rot_fail_threshold;
+  // 2nd-order Butterworth low-pass, cutoff 4 Hz at fs = 1/(sim_dt * action_repeat), bilinear transform
+  // (scipy.signal.butter(2, [4/(0.5 fs)]) as used by action_filter.py:42-44, 196-217)
+  const double fs = 1.0 / (c.sim_time_step * c.action_repeat);
+  const double wn = 4.0 / (0.5 * fs);
+  const double K = tan(M_PI * wn / 2.0);
+  const double norm = 1.0 / (1.0 + M_SQRT2 * K + K * K);
+  d.fb0 = (float)(K * K * norm); d.fb1 = (float)(2.0 * K * K * norm); d.fb2 = d.fb0;
+  d.fa1 = (float)(2.0 * (K * K - 1.0) * norm); d.fa2 = (float)((1.0 - M_SQRT2 * K + K * K) * norm);
+  d.phys.dt = (float)c.sim_time_step; d.phys.g = -c.gravity_z;
+  d.phys.kn = c.contact_kn; d.phys.bn = c.contact_bn; d.phys.d0 = c.contact_d0; d.phys.bt = c.contact_bt;
+  d.phys.klim = c.limit_k; d.phys.dlim = c.limit_d; d.phys.e0 = c.limit_e0;
+}
+
+extern "C" int orl_create(const orl_config* cfg, const orl_robot_model* model, orl_env** out) {
+  if (!cfg || !model || !out) return ORL_ERR_INVALID;
+  *out = nullptr;
+  orl_env* e = new (std::nothrow) orl_env();
+  if (!e) return ORL_ERR_INVALID;
+  e->cfg = *cfg; e->model = *model; e->motions_loaded = false; e->launches = 0;
+  e->d_state = nullptr; e->d_model = nullptr; e->d_stats = nullptr;
+  e->p_act = e->p_obs = e->p_rew = nullptr; e->p_done = e->p_mask = nullptr;
+  e->d_act = e->d_obs = e->d_rew = nullptr; e->d_done = e->d_mask = nullptr;
+  e->stream = nullptr;
+  *out = e;   // returned even on failure so that orl_last_error works; the caller destroys it
+  if (cfg->abi_version != ORL_ABI_VERSION) return fail(e, ORL_ERR_INVALID, "ABI version %d != %d", cfg->abi_version, ORL_ABI_VERSION);
+  if (cfg->num_robot <= 0) return fail(e, ORL_ERR_INVALID, "num_robot must be positive");
+  if (cfg->action_repeat < 3) return fail(e, ORL_ERR_INVALID, "action_repeat must be >= 3 (control latency of 2 substeps)");
+  if (!(cfg->sim_time_step > 0)) return fail(e, ORL_ERR_INVALID, "sim_time_step must be positive");
+  if (model->n_links < 0 || model->n_links > ORL_MAX_LINKS) return fail(e, ORL_ERR_INVALID, "bad n_links");
+  for (int l = 0; l < ORL_NUM_LEGS; ++l) {
+    if (model->leg[l].n_cp < 0 || model->leg[l].n_cp > ORL_MAX_CP) return fail(e, ORL_ERR_INVALID, "bad n_cp on leg %d", l);
+    if (model->leg[l].n_ee < 0 || model->leg[l].n_ee > 2) return fail(e, ORL_ERR_INVALID, "bad n_ee on leg %d", l);
+    for (int k = 0; k < 3; ++k)
+      if (model->leg[l].motor[k] < 0 || model->leg[l].motor[k] >= 12) return fail(e, ORL_ERR_INVALID, "bad motor index");
+  }
+  e->device = cfg->device;
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  const size_t nstate = (size_t)cfg->num_robot * ORL_STRIDE;
+  CUDA_TRY(e, cudaMalloc(&e->d_state, nstate * sizeof(float)));
+  CUDA_TRY(e, cudaMemset(e->d_state, 0, nstate * sizeof(float)));
+  CUDA_TRY(e, cudaMalloc(&e->d_model, ORL_SMEM_MODEL_BYTES));
+  CUDA_TRY(e, cudaMemset(e->d_model, 0, ORL_SMEM_MODEL_BYTES));
+  CUDA_TRY(e, cudaMemcpy(e->d_model, model, sizeof(orl_robot_model), cudaMemcpyHostToDevice));
+  CUDA_TRY(e, cudaMalloc(&e->d_stats, 4 * sizeof(double)));
+  CUDA_TRY(e, cudaMemset(e->d_stats, 0, 4 * sizeof(double)));
+  // motor strengths default to 1, orientation of the control observation to identity
+  {
+    std::vector<float> init(nstate, 0.f);
+    for (int r = 0; r < cfg->num_robot; ++r) {
+      float* S = init.data() + (size_t)r * ORL_STRIDE;
+      for (int m = 0; m < 12; ++m) S[S_STRENGTH + m] = 1.f;
+      S[S_OBSQ + 3] = 1.f; S[S_OROT + 3] = 1.f; S[S_QUAT + 3] = 1.f;
+    }
+    CUDA_TRY(e, cudaMemcpy(e->d_state, init.data(), nstate * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  const int N = cfg->num_robot;
+  CUDA_TRY(e, cudaMallocHost(&e->p_act, (size_t)N * 12 * sizeof(float)));
+  CUDA_TRY(e, cudaMallocHost(&e->p_obs, (size_t)N * ORL_OBS_SIZE * sizeof(float)));
+  CUDA_TRY(e, cudaMallocHost(&e->p_rew, (size_t)N * sizeof(float)));
+  CUDA_TRY(e, cudaMallocHost(&e->p_done, (size_t)N));
+  CUDA_TRY(e, cudaMallocHost(&e->p_mask, (size_t)N));
+  CUDA_TRY(e, cudaMalloc(&e->d_act, (size_t)N * 12 * sizeof(float)));
+  CUDA_TRY(e, cudaMalloc(&e->d_obs, (size_t)N * ORL_OBS_SIZE * sizeof(float)));
+  CUDA_TRY(e, cudaMalloc(&e->d_rew, (size_t)N * sizeof(float)));
+  CUDA_TRY(e, cudaMalloc(&e->d_done, (size_t)N));
+  CUDA_TRY(e, cudaMalloc(&e->d_mask, (size_t)N));
+  CUDA_TRY(e, cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  CUDA_TRY(e, cudaFuncSetAttribute(orl_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ORL_SMEM_BYTES));
+  CUDA_TRY(e, cudaFuncSetAttribute(orl_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ORL_SMEM_BYTES));
+  e->dev.state = e->d_state; e->dev.model = e->d_model; e->dev.stats = e->d_stats;
+  memset(&e->dev.mt, 0, sizeof(e->dev.mt));
+  fill_dev_cfg(e);
+  return ORL_OK;
+}
+
+static void free_motions(orl_env* e) {
+  for (void* p : e->d_motion) cudaFree(p);
+  e->d_motion.clear();
+}
+
+extern "C" int orl_destroy(orl_env* e) {
+  if (!e) return ORL_OK;
+  cudaSetDevice(e->device);
+  free_motions(e);
+  cudaFree(e->d_state); cudaFree(e->d_model); cudaFree(e->d_stats);
+  cudaFreeHost(e->p_act); cudaFreeHost(e->p_obs); cudaFreeHost(e->p_rew); cudaFreeHost(e->p_done); cudaFreeHost(e->p_mask);
+  cudaFree(e->d_act); cudaFree(e->d_obs); cudaFree(e->d_rew); cudaFree(e->d_done); cudaFree(e->d_mask);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+  return ORL_OK;
+}
+
+template <typename T>
+static int upload(orl_env* e, const std::vector<T>& h, const T** out) {
+  void* d = nullptr;
+  CUDA_TRY(e, cudaMalloc(&d, h.size() * sizeof(T) + 16));
+  e->d_motion.push_back(d);
+  CUDA_TRY(e, cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  *out = (const T*)d;
+  return ORL_OK;
+}
+
+extern "C" int orl_load_motions(orl_env* e, const double* frames, const int32_t* n_frames, const double* frame_dur,
+                                const int32_t* flags, int32_t n_clips) {
+  if (!e) return ORL_ERR_INVALID;
+  if (n_clips <= 0) return fail(e, ORL_ERR_INVALID, "No reference motions specified.");   // imitation_task.py:583-584
+  if (!frames || !n_frames || !frame_dur || !flags) return fail(e, ORL_ERR_INVALID, "null argument");
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  free_motions(e);
+  int total = 0;
+  for (int c = 0; c < n_clips; ++c) {
+    if (n_frames[c] <= 0) return fail(e, ORL_ERR_ASSERT, "Must have at least 1 frame.");        // motion_data.py:105
+    if (!(frame_dur[c] > 0)) return fail(e, ORL_ERR_ASSERT, "Frame duration must be positive.");  // :108
+    total += n_frames[c];
+  }
+  const int FS = 19, VS = 18;
+  e->h_frames.assign(frames, frames + (size_t)total * FS);
+  e->h_vels.assign((size_t)total * VS, 0.0);
+  e->h_dur.resize(n_clips); e->h_dpos.resize((size_t)n_clips * 3); e->h_dheading.resize(n_clips);
+  e->h_nframes.assign(n_frames, n_frames + n_clips);
+  std::vector<int32_t> h_start(n_clips), h_nf(n_clips), h_flags(n_clips);
+  std::vector<double> h_fd(n_clips);
+  std::vector<float> h_cyc((size_t)n_clips * ORL_CYCLE_TABLE * 3, 0.f), h_warm((size_t)n_clips * ORL_FRAME_STRIDE, 0.f);
+  std::vector<float> h_dposf((size_t)n_clips * 3);
+  const orl_robot_model& M = e->model;
+  int off = 0;
+  for (int c = 0; c < n_clips; ++c) {
+    const int F = n_frames[c];
+    double* fr = e->h_frames.data() + (size_t)off * FS;
+    double* vl = e->h_vels.data() + (size_t)off * VS;
+    // _postprocess_frames, motion_data.py:527-556
+    const double x0 = fr[0], y0 = fr[1];
+    for (int f = 0; f < F; ++f) {
+      double* r = fr + (size_t)f * FS;
+      r[0] -= x0; r[1] -= y0;
+      const double n = sqrt(r[3] * r[3] + r[4] * r[4] + r[5] * r[5] + r[6] * r[6]);
+      if (fabs(n) <= 1e-8) return fail(e, ORL_ERR_INVALID, "Quaternion may not be zero in QuaternionNormalize");   // pose3d.py:103-107
+      for (int k = 3; k < 7; ++k) r[k] /= n;
+      if (r[6] < 0) for (int k = 3; k < 7; ++k) r[k] = -r[k];
+    }
+    // _calc_frame_vels, motion_data.py:635-680
+    const double dt = frame_dur[c];
+    for (int f = 0; f + 1 < F; ++f) {
+      const double* a = fr + (size_t)f * FS;
+      const double* b = fr + (size_t)(f + 1) * FS;
+      double* v = vl + (size_t)f * VS;
+      for (int k = 0; k < 3; ++k) v[k] = (b[k] - a[k]) / dt;
+      Qd dq = qd_mul(Qd{b[3], b[4], b[5], b[6]}, qd_conj(Qd{a[3], a[4], a[5], a[6]}));
+      // pose3d.QuaternionToAxisAngle, pose3d.py:139-187
+      double ax[3] = {dq.x, dq.y, dq.z};
+      const double an = sqrt(ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2]);
+      if (an < 1e-8) { ax[0] = 0; ax[1] = 0; ax[2] = 1; } else { ax[0] /= an; ax[1] /= an; ax[2] /= an; }
+      const double angle = atan2(an, dq.w) * 2;
+      for (int k = 0; k < 3; ++k) v[3 + k] = (angle / dt) * ax[k];
+      for (int k = 0; k < 12; ++k) v[6 + k] = (b[7 + k] - a[7 + k]) / dt;
+    }
+    if (F > 1) memcpy(vl + (size_t)(F - 1) * VS, vl + (size_t)(F - 2) * VS, VS * sizeof(double));
+    // cycle deltas, motion_data.py:558-589
+    const double* first = fr;
+    const double* last = fr + (size_t)(F - 1) * FS;
+    double dp[3] = {last[0] - first[0], last[1] - first[1], 0.0};
+    Qd drot = qd_mul(Qd{last[3], last[4], last[5], last[6]}, qd_conj(Qd{first[3], first[4], first[5], first[6]}));
+    const double dh = qd_heading(drot);
+    e->h_dur[c] = dt * (F - 1);       // motion_data.py:205-207
+    for (int k = 0; k < 3; ++k) { e->h_dpos[c * 3 + k] = dp[k]; h_dposf[c * 3 + k] = (float)dp[k]; }
+    e->h_dheading[c] = dh;
+    h_start[c] = off; h_nf[c] = F; h_flags[c] = flags[c]; h_fd[c] = dt;
+    // pre-summed rotating cycle offsets, motion_data.py:607-613
+    {
+      double acc[3] = {0, 0, 0};
+      for (int i = 0; i < ORL_CYCLE_TABLE; ++i) {
+        for (int k = 0; k < 3; ++k) h_cyc[((size_t)c * ORL_CYCLE_TABLE + i) * 3 + k] = (float)acc[k];
+        double cur[3];
+        qd_rot(qd_about_z(i * dh), dp, cur);
+        for (int k = 0; k < 3; ++k) acc[k] += cur[k];
+      }
+    }
+    // warm-up pose, imitation_task.py:985-1009 (pose0 = calc_frame(0) = frame 0 with no cycle offset)
+    {
+      Qd r0{first[3], first[4], first[5], first[6]};
+      Qd rdef{M.init_quat[0], M.init_quat[1], M.init_quat[2], M.init_quat[3]};
+      const double delta = qd_heading(r0) - qd_heading(rdef);
+      Qd drq = qd_about_z(delta);
+      double p[3] = {M.init_pos[0], M.init_pos[1], M.init_pos[2]}, pr[3];
+      qd_rot(drq, p, pr);
+      Qd rr = qd_mul(drq, rdef);
+      float* w = h_warm.data() + (size_t)c * ORL_FRAME_STRIDE;
+      w[0] = (float)pr[0]; w[1] = (float)pr[1]; w[2] = (float)pr[2];
+      w[3] = (float)rr.x; w[4] = (float)rr.y; w[5] = (float)rr.z; w[6] = (float)rr.w;
+      for (int l = 0; l < 4; ++l)
+        for (int k = 0; k < 3; ++k) {
+          const orl_leg_model& L = M.leg[l];
+          w[7 + 3 * l + k] = (L.init_angle[k] + L.offset[k]) * L.dir[k];    // minitaur.py:1190-1194
+        }
+    }
+    off += F;
+  }
+  std::vector<float> f32((size_t)total * ORL_FRAME_STRIDE, 0.f), v32((size_t)total * ORL_FRAME_STRIDE, 0.f);
+  for (int f = 0; f < total; ++f) {
+    for (int k = 0; k < FS; ++k) f32[(size_t)f * ORL_FRAME_STRIDE + k] = (float)e->h_frames[(size_t)f * FS + k];
+    for (int k = 0; k < VS; ++k) v32[(size_t)f * ORL_FRAME_STRIDE + k] = (float)e->h_vels[(size_t)f * VS + k];
+  }
+  MotionTables& T = e->dev.mt;
+  int rc;
+  if ((rc = upload(e, f32, &T.frames))) return rc;
+  if ((rc = upload(e, v32, &T.vels))) return rc;
+  if ((rc = upload(e, h_start, &T.start))) return rc;
+  if ((rc = upload(e, h_nf, &T.nframes))) return rc;
+  if ((rc = upload(e, h_flags, &T.flags))) return rc;
+  if ((rc = upload(e, h_fd, &T.fd))) return rc;
+  if ((rc = upload(e, e->h_dur, &T.dur))) return rc;
+  if ((rc = upload(e, e->h_dheading, &T.dheading))) return rc;
+  if ((rc = upload(e, h_dposf, &T.dpos))) return rc;
+  if ((rc = upload(e, h_cyc, &T.cyc_table))) return rc;
+  if ((rc = upload(e, h_warm, &T.warm_pose))) return rc;
+  T.n_clips = n_clips;
+  e->motions_loaded = true;
+  return ORL_OK;
+}
+
+extern "C" int orl_get_motion_tables(orl_env* e, double* frames_out, double* vels_out, double* duration, double* delta_pos,
+                                     double* delta_heading) {
+  if (!e) return ORL_ERR_INVALID;
+  if (!e->motions_loaded) return fail(e, ORL_ERR_STATE, "motions not loaded");
+  if (frames_out) memcpy(frames_out, e->h_frames.data(), e->h_frames.size() * sizeof(double));
+  if (vels_out) memcpy(vels_out, e->h_vels.data(), e->h_vels.size() * sizeof(double));
+  if (duration) memcpy(duration, e->h_dur.data(), e->h_dur.size() * sizeof(double));
+  if (delta_pos) memcpy(delta_pos, e->h_dpos.data(), e->h_dpos.size() * sizeof(double));
+  if (delta_heading) memcpy(delta_heading, e->h_dheading.data(), e->h_dheading.size() * sizeof(double));
+  return ORL_OK;
+}
+
+#define NEED_MOTIONS(e)                                                            \
+  do {                                                                             \
+    if (!(e)) return ORL_ERR_INVALID;                                              \
+    if (!(e)->motions_loaded) return fail(e, ORL_ERR_STATE, "motions not loaded"); \
+  } while (0)
+
+static int check_launch(orl_env* e, const char* what) {
+  cudaError_t s = cudaGetLastError();
+  if (s != cudaSuccess) return fail(e, ORL_ERR_CUDA, "%s launch failed: %s", what, cudaGetErrorString(s));
+  e->launches++;
+  return ORL_OK;
+}
+
+extern "C" int orl_reset(orl_env* e, const uint8_t* mask_dev, float* obs_dev, void* stream) {
+  NEED_MOTIONS(e);
+  const int blocks = (e->cfg.num_robot + ORL_ROBOTS_PER_WARP - 1) / ORL_ROBOTS_PER_WARP;
+  orl_reset_kernel<<<blocks, 32, ORL_SMEM_BYTES, (cudaStream_t)stream>>>(e->dev, mask_dev, obs_dev);
+  return check_launch(e, "orl_reset_kernel");
+}
+
+extern "C" int orl_step(orl_env* e, const float* actions_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev, void* stream) {
+  NEED_MOTIONS(e);
+  if (!actions_dev || !obs_dev || !reward_dev || !done_dev) return fail(e, ORL_ERR_INVALID, "null buffer");
+  const int blocks = (e->cfg.num_robot + ORL_ROBOTS_PER_WARP - 1) / ORL_ROBOTS_PER_WARP;
+  orl_step_kernel<<<blocks, 32, ORL_SMEM_BYTES, (cudaStream_t)stream>>>(e->dev, actions_dev, obs_dev, reward_dev, done_dev);
+  return check_launch(e, "orl_step_kernel");
+}
+
+extern "C" int orl_reset_host(orl_env* e, const uint8_t* mask, float* obs) {
+  NEED_MOTIONS(e);
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  const int N = e->cfg.num_robot;
+  if (mask) {
+    memcpy(e->p_mask, mask, N);
+    CUDA_TRY(e, cudaMemcpyAsync(e->d_mask, e->p_mask, N, cudaMemcpyHostToDevice, e->stream));
+  }
+  int rc = orl_reset(e, mask ? e->d_mask : nullptr, e->d_obs, e->stream);
+  if (rc) return rc;
+  CUDA_TRY(e, cudaMemcpyAsync(e->p_obs, e->d_obs, (size_t)N * ORL_OBS_SIZE * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+  if (obs) memcpy(obs, e->p_obs, (size_t)N * ORL_OBS_SIZE * sizeof(float));
+  return ORL_OK;
+}
+
+extern "C" int orl_step_host(orl_env* e, const float* actions, float* obs, float* reward, uint8_t* done) {
+  NEED_MOTIONS(e);
+  if (!actions || !obs || !reward || !done) return fail(e, ORL_ERR_INVALID, "null buffer");
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  const int N = e->cfg.num_robot;
+  memcpy(e->p_act, actions, (size_t)N * 12 * sizeof(float));
+  CUDA_TRY(e, cudaMemcpyAsync(e->d_act, e->p_act, (size_t)N * 12 * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+  int rc = orl_step(e, e->d_act, e->d_obs, e->d_rew, e->d_done, e->stream);
+  if (rc) return rc;
+  CUDA_TRY(e, cudaMemcpyAsync(e->p_obs, e->d_obs, (size_t)N * ORL_OBS_SIZE * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(e, cudaMemcpyAsync(e->p_rew, e->d_rew, (size_t)N * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(e, cudaMemcpyAsync(e->p_done, e->d_done, (size_t)N, cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+  memcpy(obs, e->p_obs, (size_t)N * ORL_OBS_SIZE * sizeof(float));
+  memcpy(reward, e->p_rew, (size_t)N * sizeof(float));
+  memcpy(done, e->p_done, (size_t)N);
+  return ORL_OK;
+}
+
+extern "C" int orl_set_max_episode_steps(orl_env* e, int32_t steps) {
+  if (!e) return ORL_ERR_INVALID;
+  if (steps <= 0) return fail(e, ORL_ERR_INVALID, "max_episode_steps must be positive");
+  e->cfg.max_episode_steps = steps;
+  e->dev.cfg.max_episode_steps = steps;
+  return ORL_OK;
+}
+
+extern "C" int orl_set_ref_state_init_prob(orl_env* e, double prob) {
+  if (!e) return ORL_ERR_INVALID;
+  e->cfg.ref_state_init_prob = prob;
+  e->dev.cfg.rsi_prob = prob;
+  return ORL_OK;
+}
+
+extern "C" int orl_state_layout_get(const orl_env* e, orl_state_layout* o) {
+  if (!e || !o) return ORL_ERR_INVALID;
+  o->stride = ORL_STRIDE;
+  o->pos = S_POS; o->quat = S_QUAT; o->q = S_Q; o->lin = S_LIN; o->ang = S_ANG; o->qd = S_QD;
+  o->filt_x = S_FX; o->filt_y = S_FY; o->prev_filtered = S_PREV; o->ring1 = S_RING1; o->ring2 = S_RING2;
+  o->imu_hist = S_IMU; o->act_hist = S_ACT; o->ang_hist = S_ANGH;
+  o->ref_pose = S_REFPOSE; o->ref_vel = S_REFVEL; o->origin_pos = S_OPOS; o->origin_rot = S_OROT;
+  o->time_offset = S_TOFF; o->prev_phase = S_PPHASE;
+  o->clip = S_CLIP; o->warmup = S_WARM; o->substep_counter = S_SUBSTEP; o->step_counter = S_STEP;
+  o->env_step_counter = S_ENVSTEP; o->episode = S_EPISODE; o->ep_return = S_EPRET; o->obs_quat = S_OBSQ;
+  o->motor_strength = S_STRENGTH;
+  return ORL_OK;
+}
+
+extern "C" int orl_state_ptr(orl_env* e, float** state_dev) {
+  if (!e || !state_dev) return ORL_ERR_INVALID;
+  *state_dev = e->d_state;
+  return ORL_OK;
+}
+
+extern "C" int orl_get_state_host(orl_env* e, float* state) {
+  if (!e || !state) return ORL_ERR_INVALID;
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  CUDA_TRY(e, cudaDeviceSynchronize());
+  CUDA_TRY(e, cudaMemcpy(state, e->d_state, (size_t)e->cfg.num_robot * ORL_STRIDE * sizeof(float), cudaMemcpyDeviceToHost));
+  return ORL_OK;
+}
+
+extern "C" int orl_set_state_host(orl_env* e, const float* state) {
+  if (!e || !state) return ORL_ERR_INVALID;
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  CUDA_TRY(e, cudaDeviceSynchronize());
+  CUDA_TRY(e, cudaMemcpy(e->d_state, state, (size_t)e->cfg.num_robot * ORL_STRIDE * sizeof(float), cudaMemcpyHostToDevice));
+  return ORL_OK;
+}
+
+extern "C" int orl_stats(orl_env* e, double out[4], int32_t reset_after) {
+  if (!e || !out) return ORL_ERR_INVALID;
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  CUDA_TRY(e, cudaDeviceSynchronize());
+  CUDA_TRY(e, cudaMemcpy(out, e->d_stats, 4 * sizeof(double), cudaMemcpyDeviceToHost));
+  if (reset_after) CUDA_TRY(e, cudaMemset(e->d_stats, 0, 4 * sizeof(double)));
+  return ORL_OK;
+}
+
+extern "C" int orl_motion_lookup(orl_env* e, const int32_t* clip_dev, const double* time_dev, int32_t n, int32_t* f0_dev,
+                                 int32_t* f1_dev, int32_t* cycle_dev, double* blend_dev, float* pose_dev, float* vel_dev,
+                                 void* stream) {
+  NEED_MOTIONS(e);
+  if (n <= 0) return ORL_OK;
+  orl_motion_lookup_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(e->dev.mt, clip_dev, time_dev, n, f0_dev, f1_dev,
+                                                                             cycle_dev, blend_dev, pose_dev, vel_dev);
+  return check_launch(e, "orl_motion_lookup_kernel");
+}
+
+extern "C" int orl_fk(orl_env* e, const float* pose_dev, int32_t n, float* com_dev, void* stream) {
+  if (!e) return ORL_ERR_INVALID;
+  if (n <= 0) return ORL_OK;
+  orl_fk_kernel<<<(n * 4 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(e->d_model, pose_dev, n, com_dev);
+  return check_launch(e, "orl_fk_kernel");
+}
+
+static int dyn_call(orl_env* e, int mode, const float* pose, const float* vel, const float* in, int n, float* out, void* stream) {
+  if (!e) return ORL_ERR_INVALID;
+  if (n <= 0) return ORL_OK;
+  if (mode == 0) CUDA_TRY(e, cudaMemsetAsync(out, 0, (size_t)n * 324 * sizeof(float), (cudaStream_t)stream));
+  orl_dyn_kernel<<<(n * 4 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(e->d_model, e->dev.cfg.phys, mode, pose, vel, in, n, out);
+  return check_launch(e, "orl_dyn_kernel");
+}
+extern "C" int orl_mass_matrix(orl_env* e, const float* pose_dev, int32_t n, float* M_dev, void* stream) {
+  return dyn_call(e, 0, pose_dev, nullptr, nullptr, n, M_dev, stream);
+}
+extern "C" int orl_inverse_dynamics(orl_env* e, const float* pose_dev, const float* vel_dev, const float* acc_dev, int32_t n,
+                                    float* tau_dev, void* stream) {
+  return dyn_call(e, 1, pose_dev, vel_dev, acc_dev, n, tau_dev, stream);
+}
+extern "C" int orl_forward_dynamics(orl_env* e, const float* pose_dev, const float* vel_dev, const float* tau_dev, int32_t n,
+                                    float* acc_dev, void* stream) {
+  return dyn_call(e, 2, pose_dev, vel_dev, tau_dev, n, acc_dev, stream);
+}
+extern "C" int orl_reward_terms(orl_env* e, float* terms_dev, void* stream) {
+  NEED_MOTIONS(e);
+  const int n = e->cfg.num_robot;
+  orl_reward_terms_kernel<<<(n * 4 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(e->dev, terms_dev);
+  return check_launch(e, "orl_reward_terms_kernel");
+}

@@ -1,0 +1,629 @@
+// The fused control-step kernel, the reset kernel and the parity entry-point kernels.
+//
+// Thread mapping: one lane per leg, 4 lanes (a "quad") per robot, 8 robots per warp, one warp per
+// thread block.  The 8 robots of a warp are one contiguous chunk of the [N][ORL_STRIDE] state array:
+// it is loaded with coalesced float4 accesses into shared memory, the 33 physics substeps run out of
+// registers, and the record plus the 160-float observation rows are written back the same way.
+#pragma once
+#include "orl_math.cuh"
+#include "orl_motion.cuh"
+#include "orl_dynamics.cuh"
+#include "orl_state.h"
+
+struct DevCfg {
+  int n;                      // robots on this device
+  int gid0;
+  unsigned long long seed;
+  int action_repeat;
+  int max_episode_steps;
+  int auto_reset;
+  int cycle_sync;
+  double sim_dt, env_dt, warmup_time, rsi_prob;
+  int tar_steps[ORL_NUM_TAR_FRAMES];
+  float w_pose, w_vel, w_ee, w_root, w_rootvel;
+  float s_pose, s_vel, s_ee, s_eeh, s_root, s_rootvel;
+  float dist_thr2, rot_thr;
+  float fb0, fb1, fb2, fa1, fa2;   // Butterworth (action_filter.py:129-217)
+  PhysParams phys;
+};
+
+struct DevEnv {
+  float* state;                       // [n][ORL_STRIDE]
+  const orl_robot_model* model;       // device copy
+  MotionTables mt;
+  DevCfg cfg;
+  double* stats;                      // [4]
+};
+
+#define ORL_SMEM_MODEL_BYTES ((sizeof(orl_robot_model) + 15) / 16 * 16)
+#define ORL_SMEM_BYTES (ORL_SMEM_MODEL_BYTES + ORL_ROBOTS_PER_WARP * (ORL_STRIDE + ORL_OBS_SIZE) * 4)
+
+ORL_DI int& as_int(float& f) { return *reinterpret_cast<int*>(&f); }
+ORL_DI double ld_f64(const float* p) { return *reinterpret_cast<const double*>(p); }
+ORL_DI void st_f64(float* p, double v) { *reinterpret_cast<double*>(p) = v; }
+
+// ---- shared-memory staging ---------------------------------------------------------------------
+ORL_DI void stage_in(const DevEnv& E, unsigned char* smem, const orl_robot_model*& Mo, float*& st, float*& ob) {
+  const int lane = threadIdx.x;
+  float4* m4 = reinterpret_cast<float4*>(smem);
+  const float4* g4 = reinterpret_cast<const float4*>(E.model);
+  for (int i = lane; i < (int)(ORL_SMEM_MODEL_BYTES / 16); i += 32)
+    if ((size_t)i * 16 < sizeof(orl_robot_model)) m4[i] = g4[i];
+  Mo = reinterpret_cast<const orl_robot_model*>(smem);
+  st = reinterpret_cast<float*>(smem + ORL_SMEM_MODEL_BYTES);
+  ob = st + ORL_ROBOTS_PER_WARP * ORL_STRIDE;
+  const int row0 = blockIdx.x * ORL_ROBOTS_PER_WARP;
+  const int R4 = ORL_STRIDE / 4;
+  const float4* s4 = reinterpret_cast<const float4*>(E.state);
+  float4* d4 = reinterpret_cast<float4*>(st);
+  for (int i = lane; i < ORL_ROBOTS_PER_WARP * R4; i += 32) {
+    const int row = min(row0 + i / R4, E.cfg.n - 1);
+    d4[i] = s4[(size_t)row * R4 + (i % R4)];
+  }
+  __syncwarp();
+}
+ORL_DI void stage_out(const DevEnv& E, const float* st, const float* ob, float* obs_out) {
+  __syncwarp();
+  const int lane = threadIdx.x;
+  const int row0 = blockIdx.x * ORL_ROBOTS_PER_WARP;
+  const int R4 = ORL_STRIDE / 4;
+  float4* s4 = reinterpret_cast<float4*>(E.state);
+  const float4* d4 = reinterpret_cast<const float4*>(st);
+  for (int i = lane; i < ORL_ROBOTS_PER_WARP * R4; i += 32) {
+    const int row = row0 + i / R4;
+    if (row < E.cfg.n) s4[(size_t)row * R4 + (i % R4)] = d4[i];
+  }
+  if (obs_out) {
+    const int O4 = ORL_OBS_SIZE / 4;
+    float4* o4 = reinterpret_cast<float4*>(obs_out);
+    const float4* b4 = reinterpret_cast<const float4*>(ob);
+    for (int i = lane; i < ORL_ROBOTS_PER_WARP * O4; i += 32) {
+      const int row = row0 + i / O4;
+      if (row < E.cfg.n) o4[(size_t)row * O4 + (i % O4)] = b4[i];
+    }
+  }
+}
+
+// ---- helpers on the staged record ----------------------------------------------------------------
+ORL_DI float3 ld3(const float* p) { return v3(p[0], p[1], p[2]); }
+ORL_DI Q4 ldq(const float* p) { return q4(p[0], p[1], p[2], p[3]); }
+ORL_DI void st3(float* p, float3 v) { p[0] = v.x; p[1] = v.y; p[2] = v.z; }
+ORL_DI void stq(float* p, Q4 q) { p[0] = q.x; p[1] = q.y; p[2] = q.z; p[3] = q.w; }
+
+ORL_DI RefFrame load_ref_frame(float* S, const DevCfg& C) {
+  RefFrame F;
+  F.clip = as_int(S[S_CLIP]);
+  F.warmup = as_int(S[S_WARM]) != 0;
+  F.warmup_time = C.warmup_time;
+  F.origin_rot = ldq(S + S_OROT);
+  F.origin_pos = ld3(S + S_OPOS);
+  return F;
+}
+// ImitationTask._get_motion_time (imitation_task.py:831-848); episode_start_time_offset is -0.0
+ORL_DI double motion_time(float* S, const DevCfg& C) {
+  double t = __dmul_rn((double)as_int(S[S_SUBSTEP]), C.sim_dt);
+  t = __dadd_rn(t, ld_f64(S + S_TOFF));
+  t = __dadd_rn(t, -0.0);
+  if (as_int(S[S_WARM])) t = __dsub_rn(t, C.warmup_time);
+  return t;
+}
+ORL_DI M3 pickR(const LegFK& K, int kb) { return kb == 0 ? K.R[0] : (kb == 1 ? K.R[1] : K.R[2]); }
+ORL_DI float3 pickp(const LegFK& K, int kb) { return kb == 0 ? K.p[0] : (kb == 1 ? K.p[1] : K.p[2]); }
+
+// Observation rows: sensor histories (already in the record) + the target frames.
+// ImitationTask.build_target_obs (imitation_task.py:254-301): lane j of the quad builds frame j.
+ORL_DI void build_obs(float* S, float* O, const DevEnv& E, int leg) {
+  const DevCfg& C = E.cfg;
+  for (int i = leg; i < 84; i += 4) O[i] = S[S_IMU + i];
+  const RefFrame F = load_ref_frame(S, C);
+  const double t0 = motion_time(S, C);
+  const float3 ref_base = ld3(S + S_REFPOSE);
+  // robot.get_base_orientation(): delayed orientation -> euler -> quaternion (minitaur.py:513-527, 630-638)
+  float roll, pitch, yaw;
+  bullet_euler(ldq(S + S_OBSQ), roll, pitch, yaw);
+  const float heading = qheading(bullet_quat_from_euler(roll, pitch, yaw));
+  float sh, ch;
+  sincosf(-heading, &sh, &ch);
+  float shh, chh;
+  sincosf(-0.5f * heading, &shh, &chh);
+  const Q4 inv_rot = q4(0.f, 0.f, shh, chh);
+  const double tt = __dadd_rn(t0, __dmul_rn((double)C.tar_steps[leg], C.env_dt));
+  const RefSample s = ref_sample(E.mt, F, tt);
+  float3 p; Q4 r;
+  ref_root(E.mt, F, s, true, p, r);
+  p = qrot_z(sh, ch, p - ref_base);
+  r = qstd(qmul(inv_rot, r));
+  float* o = O + 84 + 19 * leg;
+  st3(o, p); stq(o + 3, r);
+#pragma unroll 4
+  for (int j = 0; j < 12; ++j) o[7 + j] = ref_joint(E.mt, F, s, j);
+}
+
+// Episode reset of one robot, executed by its quad on the staged record.
+// Minitaur.reset (minitaur.py:232-278) + ImitationTask.reset/_reset_ref_motion/_sync_sim_model
+// (imitation_task.py:166-199, 694-732, 778-793).  `qmask` = the 4 lanes of this quad.
+ORL_DI void reset_robot(float* S, const DevEnv& E, const orl_robot_model& Mo, int gid, int leg, unsigned qmask) {
+  const DevCfg& C = E.cfg;
+  const orl_leg_model& L = Mo.leg[leg];
+  const int episode = as_int(S[S_EPISODE]);
+  uint32_t ra[4], rb[4];
+  philox4x32((uint32_t)gid, (uint32_t)episode, 0u, 0u, (uint32_t)(C.seed & 0xffffffffull), (uint32_t)(C.seed >> 32), ra);
+  philox4x32((uint32_t)gid, (uint32_t)episode, 1u, 0u, (uint32_t)(C.seed & 0xffffffffull), (uint32_t)(C.seed >> 32), rb);
+  const double u_rsi = u01_53(ra[0], ra[1]);
+  const int clip = (int)(((unsigned long long)ra[2] * (unsigned long long)E.mt.n_clips) >> 32);
+  const double u_time = u01_53(rb[0], rb[1]);
+  const bool ref_init = u_rsi < C.rsi_prob;                          // imitation_task.py:183-184
+  const bool warm = !ref_init && C.warmup_time > 0.0;                 // :186-188
+  const double toff = warm ? __dadd_rn(0.0, __dmul_rn(__dsub_rn(C.warmup_time, 0.0), u_time))
+                           : __dadd_rn(0.0, __dmul_rn(__dsub_rn(E.mt.dur[clip], 0.0), u_time));   // :1103-1123
+  __syncwarp(qmask);
+  // per-motor fields owned by this lane
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int m = L.motor[k];
+    const float qm_def = L.init_angle[k] * L.dir[k];                // true motor angle of the default pose
+    S[S_FX + m] = 0.f; S[S_FX + 12 + m] = 0.f; S[S_FY + m] = 0.f; S[S_FY + 12 + m] = 0.f;   // action_filter.py:103-109
+    S[S_PREV + m] = 0.f;
+    S[S_RING1 + m] = qm_def; S[S_RING2 + m] = qm_def;
+#pragma unroll
+    for (int h = 0; h < 3; ++h) { S[S_ACT + 12 * h + m] = 0.f; S[S_ANGH + 12 * h + m] = wrap_pi(qm_def); }
+  }
+  if (leg == 0) {
+    for (int i = 0; i < 12; ++i) S[S_IMU + i] = 0.f;
+    as_int(S[S_CLIP]) = clip;
+    as_int(S[S_WARM]) = warm ? 1 : 0;
+    as_int(S[S_SUBSTEP]) = 0; as_int(S[S_STEP]) = 0; as_int(S[S_ENVSTEP]) = 0;
+    as_int(S[S_EPISODE]) = episode + 1;
+    S[S_EPRET] = 0.f;
+    st_f64(S + S_TOFF, toff);
+    stq(S + S_OBSQ, q4(0.f, 0.f, 0.f, 1.f));
+  }
+  // _reset_ref_motion
+  RefFrame F;
+  F.clip = clip; F.warmup = warm; F.warmup_time = C.warmup_time;
+  F.origin_rot = q4(0.f, 0.f, 0.f, 1.f); F.origin_pos = v3(0.f, 0.f, 0.f);
+  double time = __dadd_rn(__dadd_rn(__dmul_rn(0.0, C.sim_dt), toff), -0.0);
+  if (warm) time = __dsub_rn(time, C.warmup_time);
+  const RefSample s = ref_sample(E.mt, F, time);
+  float3 p0; Q4 r0;
+  ref_root(E.mt, F, s, true, p0, r0);
+  const float3 sim_pos = ld3(Mo.init_pos);
+  const Q4 sim_rot = ldq(Mo.init_quat);
+  float3 op = sim_pos - p0; op.z = 0.f;
+  const float dh = qheading(sim_rot) - qheading(r0);
+  F.origin_pos = op;
+  F.origin_rot = qaxis_z(dh);
+  float3 rp, rl, ra3; Q4 rq;
+  ref_root(E.mt, F, s, true, rp, rq);
+  ref_root_vel(E.mt, F, s, rl, ra3);
+  if (leg == 0) {
+    st3(S + S_OPOS, F.origin_pos); stq(S + S_OROT, F.origin_rot);
+    st3(S + S_REFPOSE, rp); stq(S + S_REFPOSE + 3, rq);
+    st3(S + S_REFVEL, rl); st3(S + S_REFVEL + 3, ra3);
+    st_f64(S + S_PPHASE, motion_phase(E.mt, clip, time));
+    // _sync_sim_model
+    st3(S + S_POS, rp); stq(S + S_QUAT, rq); st3(S + S_LIN, rl); st3(S + S_ANG, ra3);
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int j = 3 * leg + k;
+    const float qj = ref_joint(E.mt, F, s, j), vj = ref_joint_vel(E.mt, F, s, j);
+    S[S_REFPOSE + 7 + j] = qj; S[S_REFVEL + 6 + j] = vj;
+    S[S_Q + j] = qj; S[S_QD + j] = vj;
+  }
+  __syncwarp(qmask);
+}
+
+// =================================================================================================
+// The fused control step (WrapperEnv.step): SURVEY.md A.3 steps 1-7.
+// =================================================================================================
+__global__ void __launch_bounds__(32) orl_step_kernel(DevEnv E, const float* __restrict__ actions, float* __restrict__ obs_out,
+                                                      float* __restrict__ reward_out, uint8_t* __restrict__ done_out) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const orl_robot_model* Mo; float* st; float* ob;
+  stage_in(E, smem, Mo, st, ob);
+  const DevCfg& C = E.cfg;
+  const int lane = threadIdx.x, leg = lane & 3, rw = lane >> 2;
+  const int robot = blockIdx.x * ORL_ROBOTS_PER_WARP + rw;
+  const bool valid = robot < C.n;
+  const int robot_c = min(robot, C.n - 1);
+  float* S = st + rw * ORL_STRIDE;
+  float* O = ob + rw * ORL_OBS_SIZE;
+  const orl_leg_model& L = Mo->leg[leg];
+  const PhysParams P = C.phys;
+
+  // ---- registers -----------------------------------------------------------------------------
+  float3 pos = ld3(S + S_POS), lin = ld3(S + S_LIN), ang = ld3(S + S_ANG);
+  Q4 quat = ldq(S + S_QUAT);
+  float q[3], qd[3], target[3], act[3], prevf[3], r1[3], r2[3], strength[3];
+  int mi[3];
+  const int substep0 = as_int(S[S_SUBSTEP]);
+  const bool first_step = as_int(S[S_STEP]) == 0;
+  // 1. set_act: a += INIT; Butterworth (minitaur.py:280-285, 1169-1178; action_filter.py:111-127)
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int m = L.motor[k];
+    mi[k] = m;
+    q[k] = S[S_Q + 3 * leg + k]; qd[k] = S[S_QD + 3 * leg + k];
+    r1[k] = S[S_RING1 + m]; r2[k] = S[S_RING2 + m];
+    prevf[k] = S[S_PREV + m]; strength[k] = S[S_STRENGTH + m];
+    act[k] = __ldg(actions + (size_t)robot_c * 12 + m) + L.init_angle[k];
+    float x0 = S[S_FX + m], x1 = S[S_FX + 12 + m], y0 = S[S_FY + m], y1 = S[S_FY + 12 + m];
+    if (substep0 == 0) { const float d = wrap_pi(r2[k]); x0 = x1 = y0 = y1 = d; }
+    const float y = act[k] * C.fb0 + (x0 * C.fb1 + x1 * C.fb2) - (y0 * C.fa1 + y1 * C.fa2);
+    S[S_FX + m] = act[k]; S[S_FX + 12 + m] = x0; S[S_FY + m] = y; S[S_FY + 12 + m] = y0;
+    target[k] = y;
+  }
+  // 2. physics substeps (quadruped_gym_env.py:220-225)
+  Q4 obs_q = ldq(S + S_OBSQ);
+  float3 obs_w = v3(0.f, 0.f, 0.f);
+  const Q4 init_inv = qconj(ldq(Mo->init_quat));
+  const int AR = C.action_repeat;
+  const float inv_ar = 1.0f / (float)AR;
+  for (int s = 0; s < AR; ++s) {
+    const float lerp = (float)(s + 1) * inv_ar;
+    const M3 Rb = qmat(quat);
+    float tau[3], qm_now[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float qobs = wrap_pi(r2[k]);                               // get_motor_angles(): delayed + wrapped
+      const float prev = first_step ? qobs : prevf[k];                 // minitaur.py:450-453
+      float cmd = prev + lerp * (target[k] - prev);                    // :455-456
+      cmd = fminf(fmaxf(cmd, qobs - Mo->max_angle_change), qobs + Mo->max_angle_change);   // :706-723
+      const float qm = (q[k] - L.offset[k]) * L.dir[k];                // :549-553
+      const float qdm = qd[k] * L.dir[k];                              // :575-578
+      const float tm = strength[k] * (-1.0f * (L.kp[k] * (qm - cmd)) - L.kd[k] * qdm);     // minitaur_motor.py:163-166
+      const float e = fmaxf(0.f, L.lower[k] - q[k]) - fmaxf(0.f, q[k] - L.upper[k]);
+      tau[k] = tm * L.dir[k] + P.klim * e - P.dlim * fminf(1.0f, fabsf(e) / P.e0) * qd[k] - L.damping[k] * qd[k];
+      qm_now[k] = qm;
+    }
+    float3 alpha, alin; float qdd[3];
+    leg_dynamics<true, false>(L, *Mo, P, Rb, pos.z, ang, lin, q, qd, tau, alpha, alin, qdd, nullptr);
+    // semi-implicit Euler: velocities first, then positions with the new velocities
+    const float3 lin_dot = alin + cross(ang, lin);
+    ang = ang + P.dt * alpha;
+    lin = lin + P.dt * lin_dot;
+    pos = pos + P.dt * lin;
+    {
+      const float wn = sqrtf(dot(ang, ang));
+      const float half = 0.5f * wn * P.dt;
+      float sh, ch;
+      sincosf(half, &sh, &ch);
+      const float kk = wn > 1e-12f ? sh / wn : 0.5f * P.dt;
+      quat = qnormalize(qmul(q4(ang.x * kk, ang.y * kk, ang.z * kk, ch), quat));
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      qd[k] += P.dt * qdd[k];
+      q[k] += P.dt * qd[k];
+      r2[k] = r1[k]; r1[k] = qm_now[k];
+    }
+    if (s == AR - 3) {   // the control observation at the end of the step is 2 substeps old (minitaur.py:336-357)
+      obs_q = qmul(quat, init_inv);                                    // :325-331
+      obs_w = qrot(qconj(obs_q), ang);                                 // :652-672
+    }
+  }
+  // ---- write the dynamic state back to the record ---------------------------------------------------
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    S[S_Q + 3 * leg + k] = q[k]; S[S_QD + 3 * leg + k] = qd[k];
+    S[S_RING1 + mi[k]] = r1[k]; S[S_RING2 + mi[k]] = r2[k];
+    S[S_PREV + mi[k]] = target[k];                                     // minitaur.py:291-292
+    // 3. sensors.on_step (sensor_wrappers.py:131-135): newest first
+    S[S_ACT + 24 + mi[k]] = S[S_ACT + 12 + mi[k]]; S[S_ACT + 12 + mi[k]] = S[S_ACT + mi[k]]; S[S_ACT + mi[k]] = act[k];
+    S[S_ANGH + 24 + mi[k]] = S[S_ANGH + 12 + mi[k]]; S[S_ANGH + 12 + mi[k]] = S[S_ANGH + mi[k]];
+    S[S_ANGH + mi[k]] = wrap_pi(r2[k]);
+  }
+  const int substep1 = substep0 + AR;
+  const int envstep1 = as_int(S[S_ENVSTEP]) + 1;
+  if (leg == 0) {
+    st3(S + S_POS, pos); stq(S + S_QUAT, quat); st3(S + S_LIN, lin); st3(S + S_ANG, ang);
+    stq(S + S_OBSQ, obs_q);
+    as_int(S[S_SUBSTEP]) = substep1;
+    as_int(S[S_STEP]) = as_int(S[S_STEP]) + 1;
+    as_int(S[S_ENVSTEP]) = envstep1;
+    float roll, pitch, yaw;
+    bullet_euler(obs_q, roll, pitch, yaw);                             // IMUSensor channels R, P, dR, dP
+    for (int i = 11; i >= 4; --i) S[S_IMU + i] = S[S_IMU + i - 4];
+    S[S_IMU + 0] = roll; S[S_IMU + 1] = pitch; S[S_IMU + 2] = obs_w.x; S[S_IMU + 3] = obs_w.y;
+  }
+  // 4. reward against the reference state of the END of the previous step (imitation_task.py:341-516)
+  const M3 Rb = qmat(quat);
+  LegFK Ks, Kr;
+  leg_fk(L, Rb, q, Ks);
+  const float3 rp = ld3(S + S_REFPOSE);
+  const Q4 rq = ldq(S + S_REFPOSE + 3);
+  float rj[3];
+  float pose_err = 0.f, vel_err = 0.f, ee_err = 0.f;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    rj[k] = S[S_REFPOSE + 7 + 3 * leg + k];
+    const float dq = rj[k] - q[k], dv = S[S_REFVEL + 6 + 3 * leg + k] - qd[k];
+    pose_err += dq * dq; vel_err += dv * dv;
+  }
+  leg_fk(L, qmat(rq), rj, Kr);
+  {
+    const Q4 inv_def = qconj(ldq(Mo->init_quat));                      // default root rotation, :1071-1075, 1245-1252
+    float ss, cs, sr, cr;
+    sincosf(-qheading(qmul(quat, inv_def)), &ss, &cs);
+    sincosf(-qheading(qmul(rq, inv_def)), &sr, &cr);
+    for (int e = 0; e < L.n_ee; ++e) {
+      const int kb = L.ee_body[e];
+      const float3 loc = ld3(L.ee_local[e]);
+      const float3 es = pickp(Ks, kb) + mul(pickR(Ks, kb), loc);       // rel. sim root
+      const float3 er = pickp(Kr, kb) + mul(pickR(Kr, kb), loc);       // rel. ref root
+      const float3 d = qrot_z(sr, cr, er) - qrot_z(ss, cs, es);
+      const float dh = (rp.z + er.z) - (pos.z + es.z);
+      ee_err += d.x * d.x + d.y * d.y + C.s_eeh * dh * dh;
+    }
+  }
+  pose_err = quad_sum(pose_err); vel_err = quad_sum(vel_err); ee_err = quad_sum(ee_err);
+  float reward;
+  {
+    const float3 dp = rp - pos;
+    const float a = qangle_normalized(qmul(rq, qconj(quat)));
+    const float root_err = dot(dp, dp) + 0.5f * a * a;
+    const float3 dv = ld3(S + S_REFVEL) - lin, dw = ld3(S + S_REFVEL + 3) - ang;
+    const float rootvel_err = dot(dv, dv) + 0.1f * dot(dw, dw);
+    reward = C.w_pose * expf(-C.s_pose * pose_err) + C.w_vel * expf(-C.s_vel * vel_err) + C.w_ee * expf(-C.s_ee * ee_err) +
+             C.w_root * expf(-C.s_root * root_err) + C.w_rootvel * expf(-C.s_rootvel * rootvel_err);
+  }
+  __syncwarp();
+  // 5. task.update (imitation_task.py:201-207, 734-761, 1020-1055)
+  RefFrame F = load_ref_frame(S, C);
+  const double time = motion_time(S, C);
+  const double new_phase = motion_phase(E.mt, F.clip, time);
+  const RefSample smp = ref_sample(E.mt, F, time);
+  if (C.cycle_sync && new_phase < ld_f64(S + S_PPHASE)) {
+    float3 p0; Q4 r0;
+    ref_root(E.mt, F, smp, false, p0, r0);
+    float3 op = pos - qrot(F.origin_rot, p0); op.z = 0.f;
+    F.origin_pos = op;
+  }
+  float3 nrp, nrl, nra; Q4 nrq;
+  ref_root(E.mt, F, smp, true, nrp, nrq);
+  ref_root_vel(E.mt, F, smp, nrl, nra);
+  __syncwarp();
+  if (leg == 0) {
+    st3(S + S_OPOS, F.origin_pos);
+    st3(S + S_REFPOSE, nrp); stq(S + S_REFPOSE + 3, nrq); st3(S + S_REFVEL, nrl); st3(S + S_REFVEL + 3, nra);
+    st_f64(S + S_PPHASE, new_phase);
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    S[S_REFPOSE + 7 + 3 * leg + k] = ref_joint(E.mt, F, smp, 3 * leg + k);
+    S[S_REFVEL + 6 + 3 * leg + k] = ref_joint_vel(E.mt, F, smp, 3 * leg + k);
+  }
+  // 6. termination against the freshly updated reference (imitation_task.py:518-572, wrapper_env.py:78-80)
+  int fall = 0;
+  for (int i = 0; i < L.n_cp; ++i) {
+    const orl_contact_point& cp = L.cp[i];
+    if (cp.is_foot) continue;
+    const int kb = cp.body;
+    const float3 loc = ld3(cp.local);
+    const float z = pos.z + (kb < 0 ? dot(Rb.r2, loc) : pickp(Ks, kb).z + dot(pickR(Ks, kb).r2, loc)) - cp.radius - cp.margin;
+    fall |= (z < 0.f);
+  }
+  fall = quad_or(fall);      // Minitaur.step_counter > 0 always holds after a step (imitation_task.py:539)
+  int done;
+  {
+    const float3 dp = nrp - pos;
+    const float a = qangle_normalized(qmul(nrq, qconj(quat)));
+    done = motion_is_over(E.mt, F.clip, time) || fall || (dot(dp, dp) > C.dist_thr2) || (fabsf(a) > C.rot_thr);
+    done |= (envstep1 >= C.max_episode_steps);
+  }
+  __syncwarp();
+  // rollout statistics (SURVEY.md section 5 "metrics"): [sum reward, sum episode length, episodes, robot steps]
+  float ep_ret = S[S_EPRET] + reward;
+  const bool finish = done && C.auto_reset;
+  {
+    float v0 = (valid && leg == 0) ? reward : 0.f, v1 = (valid && leg == 0 && finish) ? (float)envstep1 : 0.f;
+    float v2 = (valid && leg == 0 && finish) ? 1.f : 0.f, v3_ = (valid && leg == 0) ? 1.f : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      v0 += __shfl_xor_sync(0xffffffffu, v0, o); v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+      v2 += __shfl_xor_sync(0xffffffffu, v2, o); v3_ += __shfl_xor_sync(0xffffffffu, v3_, o);
+    }
+    if (lane == 0) {
+      atomicAdd(E.stats + 0, (double)v0); atomicAdd(E.stats + 1, (double)v1);
+      atomicAdd(E.stats + 2, (double)v2); atomicAdd(E.stats + 3, (double)v3_);
+    }
+  }
+  __syncwarp();
+  if (leg == 0) S[S_EPRET] = ep_ret;
+  if (valid && leg == 0) { reward_out[robot] = reward; done_out[robot] = (uint8_t)done; }
+  __syncwarp();
+  if (finish) reset_robot(S, E, *Mo, C.gid0 + robot_c, leg, 0xFu << (lane & ~3));
+  __syncwarp();
+  // 7. observation (histories + target frames)
+  build_obs(S, O, E, leg);
+  stage_out(E, st, ob, obs_out);
+}
+
+// =================================================================================================
+__global__ void __launch_bounds__(32) orl_reset_kernel(DevEnv E, const uint8_t* __restrict__ mask, float* __restrict__ obs_out) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const orl_robot_model* Mo; float* st; float* ob;
+  stage_in(E, smem, Mo, st, ob);
+  const int lane = threadIdx.x, leg = lane & 3, rw = lane >> 2;
+  const int robot = blockIdx.x * ORL_ROBOTS_PER_WARP + rw;
+  const int robot_c = min(robot, E.cfg.n - 1);
+  float* S = st + rw * ORL_STRIDE;
+  const bool doit = mask == nullptr || mask[robot_c] != 0;
+  if (doit) reset_robot(S, E, *Mo, E.cfg.gid0 + robot_c, leg, 0xFu << (lane & ~3));
+  __syncwarp();
+  build_obs(S, ob + rw * ORL_OBS_SIZE, E, leg);
+  stage_out(E, st, ob, obs_out);
+}
+
+// ---- parity entry points --------------------------------------------------------------------------
+__global__ void orl_motion_lookup_kernel(MotionTables T, const int32_t* clip, const double* time, int n, int32_t* f0,
+                                         int32_t* f1, int32_t* cycle, double* blend, float* pose, float* vel) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int c = clip[i];
+  const BlendIdx b = motion_blend_idx(T, c, time[i]);
+  if (f0) f0[i] = b.f0;
+  if (f1) f1[i] = b.f1;
+  if (cycle) cycle[i] = b.cycle;
+  if (blend) blend[i] = b.blend;
+  if (pose) {
+    float3 p; Q4 r;
+    motion_root(T, c, b, p, r);
+    float* o = pose + (size_t)i * 19;
+    st3(o, p); stq(o + 3, r);
+    for (int j = 0; j < 12; ++j) o[7 + j] = motion_joint(T, c, b, j);
+  }
+  if (vel) {
+    float3 l, a;
+    motion_root_vel(T, c, b, l, a);
+    float* o = vel + (size_t)i * 18;
+    st3(o, l); st3(o + 3, a);
+    for (int j = 0; j < 12; ++j) o[6 + j] = motion_joint_vel(T, c, b, j);
+  }
+}
+
+// one quad per query, model read from global memory (diagnostic paths, not performance critical)
+__global__ void orl_fk_kernel(const orl_robot_model* Mo, const float* pose, int n, float* com) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = min(t >> 2, n - 1), leg = t & 3;
+  const bool valid = (t >> 2) < n;
+  const float* p = pose + (size_t)i * 19;
+  const orl_leg_model& L = Mo->leg[leg];
+  float q[3] = {p[7 + 3 * leg], p[8 + 3 * leg], p[9 + 3 * leg]};
+  LegFK K;
+  leg_fk(L, qmat(ldq(p + 3)), q, K);
+  if (!valid) return;
+  for (int l = 0; l < Mo->n_links; ++l) {
+    if (Mo->link_leg[l] != leg) continue;
+    const int kb = Mo->link_body[l];
+    const float3 c = ld3(p) + pickp(K, kb) + mul(pickR(K, kb), ld3(Mo->link_com[l]));
+    st3(com + ((size_t)i * Mo->n_links + l) * 3, c);
+  }
+}
+
+// mode 0: mass matrix [n][18][18]; 1: inverse dynamics tau [n][18]; 2: forward dynamics acc [n][18]
+// generalised velocity order of the interface: [lin(3), ang(3), joints(12)]
+__global__ void orl_dyn_kernel(const orl_robot_model* Mo, PhysParams P, int mode, const float* pose, const float* vel,
+                               const float* in, int n, float* out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = min(t >> 2, n - 1), leg = t & 3;
+  const bool valid = (t >> 2) < n;
+  const float* p = pose + (size_t)i * 19;
+  const orl_leg_model& L = Mo->leg[leg];
+  float q[3] = {p[7 + 3 * leg], p[8 + 3 * leg], p[9 + 3 * leg]};
+  float3 lin = v3(0.f, 0.f, 0.f), ang = v3(0.f, 0.f, 0.f);
+  float qd[3] = {0.f, 0.f, 0.f}, tau[3] = {0.f, 0.f, 0.f};
+  if (vel) {
+    const float* v = vel + (size_t)i * 18;
+    lin = ld3(v); ang = ld3(v + 3);
+    for (int k = 0; k < 3; ++k) qd[k] = v[6 + 3 * leg + k];
+  }
+  if (mode == 2) for (int k = 0; k < 3; ++k) tau[k] = in[(size_t)i * 12 + 3 * leg + k];
+  const M3 Rb = qmat(ldq(p + 3));
+  float3 alpha, alin; float qdd[3];
+  DynExport ex;
+  if (mode == 2) leg_dynamics<true, false>(L, *Mo, P, Rb, p[2], ang, lin, q, qd, tau, alpha, alin, qdd, nullptr);
+  else leg_dynamics<false, true>(L, *Mo, P, Rb, p[2], ang, lin, q, qd, tau, alpha, alin, qdd, &ex);
+  if (mode == 2) {
+    if (!valid) return;
+    float* o = out + (size_t)i * 18;
+    if (leg == 0) { st3(o, alin + cross(ang, lin)); st3(o + 3, alpha); }
+    for (int k = 0; k < 3; ++k) o[6 + 3 * leg + k] = qdd[k];
+    return;
+  }
+  // interface index of internal base coordinate c (internal order: ang 0..2, lin 3..5)
+  const int bi[6] = {3, 4, 5, 0, 1, 2};
+  float Fc[3][6];
+  for (int k = 0; k < 3; ++k) {
+    Fc[k][0] = ex.Fcol[k].a.x; Fc[k][1] = ex.Fcol[k].a.y; Fc[k][2] = ex.Fcol[k].a.z;
+    Fc[k][3] = ex.Fcol[k].l.x; Fc[k][4] = ex.Fcol[k].l.y; Fc[k][5] = ex.Fcol[k].l.z;
+  }
+  const int tri3[3][3] = {{0, 1, 3}, {1, 2, 4}, {3, 4, 5}};
+  if (mode == 0) {
+    if (!valid) return;
+    float* M = out + (size_t)i * 324;
+    if (leg == 0)
+      for (int a = 0; a < 6; ++a)
+        for (int b = 0; b <= a; ++b) { M[bi[a] * 18 + bi[b]] = ex.Hbb[TRI(a, b)]; M[bi[b] * 18 + bi[a]] = ex.Hbb[TRI(a, b)]; }
+    for (int k = 0; k < 3; ++k) {
+      const int jk = 6 + 3 * leg + k;
+      for (int c = 0; c < 6; ++c) { M[bi[c] * 18 + jk] = Fc[k][c]; M[jk * 18 + bi[c]] = Fc[k][c]; }
+      for (int j = 0; j < 3; ++j) M[jk * 18 + 6 + 3 * leg + j] = ex.Hll[tri3[k][j]];
+    }
+    return;
+  }
+  // mode 1: tau = H (nudot - e) + C, e = [0; w x v; 0]
+  const float* ac = in + (size_t)i * 18;
+  const float3 e = cross(ang, lin);
+  float ab[6] = {ac[3], ac[4], ac[5], ac[0] - e.x, ac[1] - e.y, ac[2] - e.z};
+  float qa[3] = {ac[6 + 3 * leg], ac[7 + 3 * leg], ac[8 + 3 * leg]};
+  float tb[6];
+  for (int c = 0; c < 6; ++c) {
+    float sacc = 0.f;
+    for (int k = 0; k < 3; ++k) sacc += Fc[k][c] * qa[k];
+    tb[c] = quad_sum(sacc);
+  }
+  if (!valid) return;
+  float* o = out + (size_t)i * 18;
+  if (leg == 0)
+    for (int a = 0; a < 6; ++a) {
+      float sacc = tb[a] + ex.pb[a];
+      for (int b = 0; b < 6; ++b) sacc += ex.Hbb[a >= b ? TRI(a, b) : TRI(b, a)] * ab[b];
+      o[bi[a]] = sacc;
+    }
+  for (int k = 0; k < 3; ++k) {
+    float sacc = ex.C[k];
+    for (int c = 0; c < 6; ++c) sacc += Fc[k][c] * ab[c];
+    for (int j = 0; j < 3; ++j) sacc += ex.Hll[tri3[k][j]] * qa[j];
+    o[6 + 3 * leg + k] = sacc;
+  }
+}
+
+// reward terms of the current state, one quad per robot, straight from global memory
+__global__ void orl_reward_terms_kernel(DevEnv E, float* terms) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = min(t >> 2, E.cfg.n - 1), leg = t & 3;
+  const bool valid = (t >> 2) < E.cfg.n;
+  const DevCfg& C = E.cfg;
+  float* S = E.state + (size_t)i * ORL_STRIDE;
+  const orl_robot_model* Mo = E.model;
+  const orl_leg_model& L = Mo->leg[leg];
+  const float3 pos = ld3(S + S_POS), lin = ld3(S + S_LIN), ang = ld3(S + S_ANG);
+  const Q4 quat = ldq(S + S_QUAT);
+  const float3 rp = ld3(S + S_REFPOSE);
+  const Q4 rq = ldq(S + S_REFPOSE + 3);
+  float q[3], rj[3], pose_err = 0.f, vel_err = 0.f, ee_err = 0.f;
+  for (int k = 0; k < 3; ++k) {
+    q[k] = S[S_Q + 3 * leg + k]; rj[k] = S[S_REFPOSE + 7 + 3 * leg + k];
+    const float dq = rj[k] - q[k], dv = S[S_REFVEL + 6 + 3 * leg + k] - S[S_QD + 3 * leg + k];
+    pose_err += dq * dq; vel_err += dv * dv;
+  }
+  LegFK Ks, Kr;
+  leg_fk(L, qmat(quat), q, Ks);
+  leg_fk(L, qmat(rq), rj, Kr);
+  const Q4 inv_def = qconj(ldq(Mo->init_quat));
+  float ss, cs, sr, cr;
+  sincosf(-qheading(qmul(quat, inv_def)), &ss, &cs);
+  sincosf(-qheading(qmul(rq, inv_def)), &sr, &cr);
+  for (int e = 0; e < L.n_ee; ++e) {
+    const int kb = L.ee_body[e];
+    const float3 loc = ld3(L.ee_local[e]);
+    const float3 es = pickp(Ks, kb) + mul(pickR(Ks, kb), loc);
+    const float3 er = pickp(Kr, kb) + mul(pickR(Kr, kb), loc);
+    const float3 d = qrot_z(sr, cr, er) - qrot_z(ss, cs, es);
+    const float dh = (rp.z + er.z) - (pos.z + es.z);
+    ee_err += d.x * d.x + d.y * d.y + C.s_eeh * dh * dh;
+  }
+  pose_err = quad_sum(pose_err); vel_err = quad_sum(vel_err); ee_err = quad_sum(ee_err);
+  const float3 dp = rp - pos;
+  const float a = qangle_normalized(qmul(rq, qconj(quat)));
+  const float root_err = dot(dp, dp) + 0.5f * a * a;
+  const float3 dv = ld3(S + S_REFVEL) - lin, dw = ld3(S + S_REFVEL + 3) - ang;
+  const float rootvel_err = dot(dv, dv) + 0.1f * dot(dw, dw);
+  if (valid && leg == 0) {
+    float* o = terms + (size_t)i * 5;
+    o[0] = expf(-C.s_pose * pose_err); o[1] = expf(-C.s_vel * vel_err); o[2] = expf(-C.s_ee * ee_err);
+    o[3] = expf(-C.s_root * root_err); o[4] = expf(-C.s_rootvel * rootvel_err);
+  }
+}

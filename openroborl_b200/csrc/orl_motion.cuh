@@ -141,22 +141,40 @@ struct RefFrame {
 
 ORL_DI bool ref_in_warmup(const RefFrame& F, double time) { return F.warmup && time >= -F.warmup_time && time < 0.0; }
 
+// One evaluation point on the reference clock: the FP64 index math is done once and shared by the
+// root / joint / velocity readers.
+struct RefSample { bool warm; BlendIdx b; };
+ORL_DI RefSample ref_sample(const MotionTables& T, const RefFrame& F, double time) {
+  RefSample s;
+  s.warm = ref_in_warmup(F, time);
+  s.b = motion_blend_idx(T, F.clip, time);
+  return s;
+}
 // ImitationTask._calc_ref_pose root part (imitation_task.py:920-953)
-ORL_DI void ref_root(const MotionTables& T, const RefFrame& F, double time, bool apply_origin, float3& pos, Q4& rot) {
-  if (ref_in_warmup(F, time)) {
+ORL_DI void ref_root(const MotionTables& T, const RefFrame& F, const RefSample& s, bool apply_origin, float3& pos, Q4& rot) {
+  if (s.warm) {
     const float* w = T.warm_pose + (size_t)F.clip * ORL_FRAME_STRIDE;
     pos = v3(w[0], w[1], w[2]); rot = q4(w[3], w[4], w[5], w[6]);
   } else {
-    BlendIdx b = motion_blend_idx(T, F.clip, time);
-    motion_root(T, F.clip, b, pos, rot);
+    motion_root(T, F.clip, s.b, pos, rot);
   }
   if (apply_origin) {
     rot = qmul(F.origin_rot, rot);
     pos = qrot(F.origin_rot, pos) + F.origin_pos;
   }
 }
-ORL_DI float ref_joint(const MotionTables& T, const RefFrame& F, double time, int j) {
-  if (ref_in_warmup(F, time)) return T.warm_pose[(size_t)F.clip * ORL_FRAME_STRIDE + 7 + j];
-  BlendIdx b = motion_blend_idx(T, F.clip, time);
-  return motion_joint(T, F.clip, b, j);
+ORL_DI float ref_joint(const MotionTables& T, const RefFrame& F, const RefSample& s, int j) {
+  if (s.warm) return T.warm_pose[(size_t)F.clip * ORL_FRAME_STRIDE + 7 + j];
+  return motion_joint(T, F.clip, s.b, j);
+}
+// ImitationTask._calc_ref_vel (imitation_task.py:955-983, 1011-1018)
+ORL_DI void ref_root_vel(const MotionTables& T, const RefFrame& F, const RefSample& s, float3& lin, float3& ang) {
+  if (s.warm) { lin = v3(0.f, 0.f, 0.f); ang = v3(0.f, 0.f, 0.f); }
+  else motion_root_vel(T, F.clip, s.b, lin, ang);
+  lin = qrot(F.origin_rot, lin);
+  ang = qrot(F.origin_rot, ang);
+}
+ORL_DI float ref_joint_vel(const MotionTables& T, const RefFrame& F, const RefSample& s, int j) {
+  if (s.warm) return 0.f;
+  return motion_joint_vel(T, F.clip, s.b, j);
 }

@@ -1,0 +1,297 @@
+"""Tensor-native batched motion-imitation environment (thin host wrapper over the C ABI).
+
+PyTorch is used only for device memory, streams and zero-copy tensor handoff; all arithmetic of the
+env step happens in the CUDA library (include/orl.h).  The list-based drop-in for the reference's
+`WrapperEnv` lives in `openroborl_b200.compat`.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _abi
+from .model import RobotModel
+from .motion import MotionClip
+
+# reference defaults: imitation_task.py:45-58 as configured by run.py:58-64
+TASK_DEFAULTS = dict(
+    pose_weight=0.5, velocity_weight=0.05, end_effector_weight=0.2, root_pose_weight=0.15, root_velocity_weight=0.1,
+    pose_err_scale=5.0, velocity_err_scale=0.1, end_effector_err_scale=40.0, end_effector_height_err_scale=3.0,
+    root_pose_err_scale=20.0, root_velocity_err_scale=2.0, tar_frame_steps=(1, 2, 10, 30), ref_state_init_prob=0.9,
+    warmup_time=0.25, enable_cycle_sync=True, dist_fail_threshold=1.0, rot_fail_threshold=0.5 * math.pi)
+# physics model of this repo (DESIGN.md "physics model"); gravity from quadruped_gym_env.py:200
+PHYS_DEFAULTS = dict(gravity_z=-10.0, contact_kn=1.0e5, contact_bn=500.0, contact_d0=0.002, contact_bt=3000.0,
+                     limit_k=1000.0, limit_d=2.0, limit_e0=0.01, mu_plane=1.0, margin_factor=0.02)
+
+_INT_FIELDS = ("clip", "warmup", "substep_counter", "step_counter", "env_step_counter", "episode")
+_F64_FIELDS = ("time_offset", "prev_phase")
+_FIELD_SHAPES = dict(
+    pos=(3,), quat=(4,), q=(12,), lin=(3,), ang=(3,), qd=(12,), filt_x=(2, 12), filt_y=(2, 12), prev_filtered=(12,),
+    ring1=(12,), ring2=(12,), imu_hist=(3, 4), act_hist=(3, 12), ang_hist=(3, 12), ref_pose=(19,), ref_vel=(18,),
+    origin_pos=(3,), origin_rot=(4,), time_offset=(), prev_phase=(), clip=(), warmup=(), substep_counter=(),
+    step_counter=(), env_step_counter=(), episode=(), ep_return=(), obs_quat=(4,), motor_strength=(12,))
+
+
+class OrlError(RuntimeError):
+    pass
+
+
+class _DevView(object):
+    """__cuda_array_interface__ holder so torch can wrap library-owned device memory without a copy."""
+
+    def __init__(self, ptr, shape, typestr, owner):
+        self.__cuda_array_interface__ = dict(shape=tuple(shape), typestr=typestr, data=(int(ptr), False), version=3, strides=None)
+        self._owner = owner
+
+
+class BatchedImitationEnv(object):
+    def __init__(self, robot="laikago", motions=None, num_robot=1, device=0, seed=0, gid0=0, auto_reset=False,
+                 max_episode_steps=600, task=None, phys=None, urdf_search_path=None):
+        if not motions:
+            raise ValueError("No reference motions specified.")           # imitation_task.py:583-584
+        self._lib = _abi.load_library()
+        self.num_robot = int(num_robot)
+        self.device = torch.device("cuda", int(device))
+        self.task = dict(TASK_DEFAULTS, **(task or {}))
+        self.phys = dict(PHYS_DEFAULTS, **(phys or {}))
+        self.model = RobotModel(robot, urdf_search_path, self.phys["mu_plane"], self.phys["margin_factor"])
+        self.clips = [m if isinstance(m, MotionClip) else MotionClip.load(m) for m in motions]
+        spec = self.model.spec
+        cfg = _abi.OrlConfig()
+        cfg.abi_version = _abi.ORL_ABI_VERSION
+        cfg.num_robot, cfg.device, cfg.gid0, cfg.seed = self.num_robot, int(device), int(gid0), int(seed)
+        cfg.action_repeat = spec.NUM_ACTION_REPEAT
+        cfg.max_episode_steps = int(max_episode_steps)
+        cfg.auto_reset = int(bool(auto_reset))
+        cfg.enable_cycle_sync = int(bool(self.task["enable_cycle_sync"]))
+        cfg.sim_time_step = spec.T_STEP
+        cfg.env_time_step = spec.NUM_ACTION_REPEAT * spec.T_STEP       # quadruped_gym_env.py:177
+        cfg.warmup_time = self.task["warmup_time"]
+        cfg.ref_state_init_prob = self.task["ref_state_init_prob"]
+        if len(self.task["tar_frame_steps"]) != _abi.NUM_TAR_FRAMES:
+            raise ValueError("tar_frame_steps must have %d entries" % _abi.NUM_TAR_FRAMES)
+        cfg.tar_frame_steps[:] = [int(v) for v in self.task["tar_frame_steps"]]
+        for k in ("pose_weight", "velocity_weight", "end_effector_weight", "root_pose_weight", "root_velocity_weight",
+                  "pose_err_scale", "velocity_err_scale", "end_effector_err_scale", "end_effector_height_err_scale",
+                  "root_pose_err_scale", "root_velocity_err_scale", "dist_fail_threshold", "rot_fail_threshold"):
+            setattr(cfg, k, float(self.task[k]))
+        for k in ("gravity_z", "contact_kn", "contact_bn", "contact_d0", "contact_bt", "limit_k", "limit_d", "limit_e0"):
+            setattr(cfg, k, float(self.phys[k]))
+        self.cfg = cfg
+        self.env_time_step = cfg.env_time_step
+        self._h = C.c_void_p()
+        rc = self._lib.orl_create(C.byref(cfg), C.byref(self.model.c), C.byref(self._h))
+        if rc != 0:
+            msg = self._lib.orl_last_error(self._h).decode() if self._h else "orl_create failed"
+            if self._h:
+                self._lib.orl_destroy(self._h)
+                self._h = C.c_void_p()
+            raise (ValueError if rc == _abi.ORL_ERR_INVALID else OrlError)(msg)
+        frames = np.concatenate([c.frames for c in self.clips], axis=0)
+        if frames.shape[1] != _abi.POSE_SIZE:
+            raise AssertionError("motion frame size %d != pose size %d" % (frames.shape[1], _abi.POSE_SIZE))  # imitation_task.py:689
+        nf = np.array([c.frames.shape[0] for c in self.clips], dtype=np.int32)
+        fd = np.array([c.frame_duration for c in self.clips], dtype=np.float64)
+        fl = np.array([c.flags for c in self.clips], dtype=np.int32)
+        frames = np.ascontiguousarray(frames, dtype=np.float64)
+        self._check(self._lib.orl_load_motions(self._h, frames.ctypes.data, nf.ctypes.data, fd.ctypes.data, fl.ctypes.data,
+                                               len(self.clips)))
+        self._total_frames = int(nf.sum())
+        lay = _abi.OrlStateLayout()
+        self._check(self._lib.orl_state_layout_get(self._h, C.byref(lay)))
+        self.layout = {n: getattr(lay, n) for n, _ in lay._fields_}
+        N = self.num_robot
+        with torch.cuda.device(self.device):
+            self.obs = torch.empty((N, _abi.OBS_SIZE), dtype=torch.float32, device=self.device)
+            self.reward = torch.empty((N,), dtype=torch.float32, device=self.device)
+            self.done = torch.empty((N,), dtype=torch.uint8, device=self.device)
+        p = C.c_void_p()
+        self._check(self._lib.orl_state_ptr(self._h, C.byref(p)))
+        self.state = torch.as_tensor(_DevView(p.value, (N, self.layout["stride"]), "<f4", self), device=self.device)
+
+    # ---- plumbing ------------------------------------------------------------------------------
+    def _check(self, rc):
+        if rc != 0:
+            msg = self._lib.orl_last_error(self._h).decode()
+            if rc == _abi.ORL_ERR_INVALID:
+                raise ValueError(msg)
+            if rc == _abi.ORL_ERR_ASSERT:
+                raise AssertionError(msg)
+            raise OrlError("orl error %d: %s" % (rc, msg))
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.orl_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- hot path (device tensors) ---------------------------------------------------------------
+    def reset(self, mask=None):
+        """mask: optional uint8/bool CUDA tensor [N]; returns the observation tensor [N,160] (reused buffer)."""
+        mp = None
+        if mask is not None:
+            mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+            mp = C.c_void_p(mask.data_ptr())
+        self._check(self._lib.orl_reset(self._h, mp, C.c_void_p(self.obs.data_ptr()), self._stream()))
+        return self.obs
+
+    def step(self, actions):
+        """actions: float32 CUDA tensor [N,12] (policy residuals).  Returns (obs, reward, done) device tensors."""
+        if actions.dtype != torch.float32 or not actions.is_cuda or not actions.is_contiguous() \
+                or tuple(actions.shape) != (self.num_robot, _abi.NUM_MOTORS):
+            raise ValueError("actions must be a contiguous float32 CUDA tensor of shape (%d, 12)" % self.num_robot)
+        self._check(self._lib.orl_step(self._h, C.c_void_p(actions.data_ptr()), C.c_void_p(self.obs.data_ptr()),
+                                       C.c_void_p(self.reward.data_ptr()), C.c_void_p(self.done.data_ptr()), self._stream()))
+        return self.obs, self.reward, self.done
+
+    # ---- hot path through host buffers (what the list-based reference API uses) -------------------
+    def reset_host(self, mask=None):
+        obs = np.empty((self.num_robot, _abi.OBS_SIZE), dtype=np.float32)
+        mp = None
+        if mask is not None:
+            mask = np.ascontiguousarray(mask, dtype=np.uint8)
+            mp = mask.ctypes.data
+        self._check(self._lib.orl_reset_host(self._h, mp, obs.ctypes.data))
+        return obs
+
+    def step_host(self, actions, out=None):
+        actions = np.ascontiguousarray(actions, dtype=np.float32)
+        if actions.shape != (self.num_robot, _abi.NUM_MOTORS):
+            raise ValueError("actions must have shape (%d, 12)" % self.num_robot)
+        if out is None:
+            out = (np.empty((self.num_robot, _abi.OBS_SIZE), dtype=np.float32), np.empty(self.num_robot, dtype=np.float32),
+                   np.empty(self.num_robot, dtype=np.uint8))
+        obs, rew, done = out
+        self._check(self._lib.orl_step_host(self._h, actions.ctypes.data, obs.ctypes.data, rew.ctypes.data, done.ctypes.data))
+        return obs, rew, done
+
+    def set_max_episode_steps(self, steps):
+        self._check(self._lib.orl_set_max_episode_steps(self._h, int(steps)))
+
+    def set_ref_state_init_prob(self, prob):
+        self._check(self._lib.orl_set_ref_state_init_prob(self._h, float(prob)))
+
+    def stats(self, reset=True):
+        out = np.zeros(4, dtype=np.float64)
+        self._check(self._lib.orl_stats(self._h, out.ctypes.data, int(reset)))
+        return out
+
+    @property
+    def launch_count(self):
+        return int(self._lib.orl_launch_count(self._h))
+
+    # ---- state import / export (checkpointing, parity tests) ------------------------------------------
+    def get_state(self):
+        N, stride = self.num_robot, self.layout["stride"]
+        raw = np.empty((N, stride), dtype=np.float32)
+        self._check(self._lib.orl_get_state_host(self._h, raw.ctypes.data))
+        out = {}
+        for name, shape in _FIELD_SHAPES.items():
+            off = self.layout[name]
+            if name in _F64_FIELDS:
+                out[name] = raw[:, off:off + 2].copy().view(np.float64)[:, 0]
+            elif name in _INT_FIELDS:
+                out[name] = raw[:, off].copy().view(np.int32)
+            else:
+                n = int(np.prod(shape)) if shape else 1
+                out[name] = raw[:, off:off + n].reshape((N,) + shape).copy()
+        return out
+
+    def set_state(self, st):
+        N, stride = self.num_robot, self.layout["stride"]
+        raw = np.empty((N, stride), dtype=np.float32)
+        self._check(self._lib.orl_get_state_host(self._h, raw.ctypes.data))
+        for name, val in st.items():
+            off = self.layout[name]
+            if name in _F64_FIELDS:
+                raw[:, off:off + 2] = np.ascontiguousarray(val, dtype=np.float64).reshape(N, 1).view(np.float32)
+            elif name in _INT_FIELDS:
+                raw[:, off] = np.ascontiguousarray(val, dtype=np.int32).view(np.float32)
+            else:
+                shape = _FIELD_SHAPES[name]
+                n = int(np.prod(shape)) if shape else 1
+                raw[:, off:off + n] = np.asarray(val, dtype=np.float32).reshape(N, n)
+        self._check(self._lib.orl_set_state_host(self._h, raw.ctypes.data))
+
+    # ---- parity entry points ------------------------------------------------------------------------
+    def motion_tables(self):
+        F, K = self._total_frames, len(self.clips)
+        frames, vels = np.empty((F, 19)), np.empty((F, 18))
+        dur, dpos, dh = np.empty(K), np.empty((K, 3)), np.empty(K)
+        self._check(self._lib.orl_get_motion_tables(self._h, frames.ctypes.data, vels.ctypes.data, dur.ctypes.data,
+                                                    dpos.ctypes.data, dh.ctypes.data))
+        return dict(frames=frames, vels=vels, duration=dur, delta_pos=dpos, delta_heading=dh)
+
+    def motion_lookup(self, clip, time):
+        clip = torch.as_tensor(np.asarray(clip, dtype=np.int32), device=self.device)
+        time = torch.as_tensor(np.asarray(time, dtype=np.float64), device=self.device)
+        n = clip.numel()
+        i32 = lambda: torch.empty(n, dtype=torch.int32, device=self.device)
+        f0, f1, cyc = i32(), i32(), i32()
+        blend = torch.empty(n, dtype=torch.float64, device=self.device)
+        pose = torch.empty((n, 19), dtype=torch.float32, device=self.device)
+        vel = torch.empty((n, 18), dtype=torch.float32, device=self.device)
+        P = lambda t: C.c_void_p(t.data_ptr())
+        self._check(self._lib.orl_motion_lookup(self._h, P(clip), P(time), n, P(f0), P(f1), P(cyc), P(blend), P(pose), P(vel),
+                                                self._stream()))
+        return dict(f0=f0.cpu().numpy(), f1=f1.cpu().numpy(), cycle=cyc.cpu().numpy(), blend=blend.cpu().numpy(),
+                    pose=pose.cpu().numpy(), vel=vel.cpu().numpy())
+
+    def _dev(self, a, cols):
+        t = torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32), device=self.device)
+        assert t.shape[1] == cols
+        return t
+
+    def fk(self, pose):
+        pose = self._dev(pose, 19)
+        n = pose.shape[0]
+        out = torch.zeros((n, self.model.num_joints, 3), dtype=torch.float32, device=self.device)
+        self._check(self._lib.orl_fk(self._h, C.c_void_p(pose.data_ptr()), n, C.c_void_p(out.data_ptr()), self._stream()))
+        return out.cpu().numpy()
+
+    def mass_matrix(self, pose):
+        pose = self._dev(pose, 19)
+        n = pose.shape[0]
+        out = torch.empty((n, 18, 18), dtype=torch.float32, device=self.device)
+        self._check(self._lib.orl_mass_matrix(self._h, C.c_void_p(pose.data_ptr()), n, C.c_void_p(out.data_ptr()), self._stream()))
+        return out.cpu().numpy()
+
+    def inverse_dynamics(self, pose, vel, acc):
+        pose, vel, acc = self._dev(pose, 19), self._dev(vel, 18), self._dev(acc, 18)
+        n = pose.shape[0]
+        out = torch.empty((n, 18), dtype=torch.float32, device=self.device)
+        self._check(self._lib.orl_inverse_dynamics(self._h, C.c_void_p(pose.data_ptr()), C.c_void_p(vel.data_ptr()),
+                                                   C.c_void_p(acc.data_ptr()), n, C.c_void_p(out.data_ptr()), self._stream()))
+        return out.cpu().numpy()
+
+    def forward_dynamics(self, pose, vel, tau):
+        pose, vel, tau = self._dev(pose, 19), self._dev(vel, 18), self._dev(tau, 12)
+        n = pose.shape[0]
+        out = torch.empty((n, 18), dtype=torch.float32, device=self.device)
+        self._check(self._lib.orl_forward_dynamics(self._h, C.c_void_p(pose.data_ptr()), C.c_void_p(vel.data_ptr()),
+                                                   C.c_void_p(tau.data_ptr()), n, C.c_void_p(out.data_ptr()), self._stream()))
+        return out.cpu().numpy()
+
+    def reward_terms(self):
+        out = torch.empty((self.num_robot, 5), dtype=torch.float32, device=self.device)
+        self._check(self._lib.orl_reward_terms(self._h, C.c_void_p(out.data_ptr()), self._stream()))
+        return out.cpu().numpy()
+
+    # ---- spaces (wrapper_env.py:127-145, minitaur.py:145-155, imitation_task.py:303-335) ---------------
+    def observation_bounds(self):
+        imu = np.array([2 * np.pi, 2 * np.pi, 2000 * np.pi, 2000 * np.pi] * 3)
+        hi = np.concatenate([imu, np.ones(36), np.pi * np.ones(36)])
+        fr = self.motion_tables()["frames"]
+        low, high = fr.min(axis=0), fr.max(axis=0)
+        low[0:3], high[0:3], low[3:7], high[3:7] = -2, 2, -1, 1
+        n = _abi.NUM_TAR_FRAMES
+        return np.concatenate([-hi, np.tile(low, n)]), np.concatenate([hi, np.tile(high, n)])

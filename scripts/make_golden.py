@@ -1,0 +1,174 @@
+"""Generate tests/golden/* from the reference tree (run in the BUILD container only).
+
+    python scripts/make_golden.py [--reference /root/reference]
+
+The GPU box has no /root/reference, so everything the tests and bench need from it is frozen here:
+
+* motion_clips.npz     : the RAW "Frames" arrays + metadata of every clip under
+                         OpenRoboRL/envs/quadruped_robot/task/motions/*.txt (input data in the reference's
+                         motion-file format, re-serialised; the JSON loader itself is exercised by re-writing
+                         these arrays to JSON at test time).
+* policy_<name>.npz    : the actor MLP (pi_fc0, pi_fc1, pi) of the reference's pretrained policy zips, used as a
+                         deterministic action source for rollouts, plus the observation-space bounds stored in
+                         the zip (pins the observation layout).
+* ref_motion_kat.npz   : known answers produced by the reference's OWN, UNMODIFIED modules
+                         (motion_data.py, pose3d.py, action_filter.py, minitaur_motor.py) imported from the
+                         reference tree with a numpy shim for the absent third-party
+                         `pybullet_utils.transformations` (oracle/xform.py restates its algorithms).
+* ref_task_trace.npz   : per-step traces (observation, reward, done, task internals) produced by the
+                         reference's own ImitationTask / Minitaur / LocomotionGymEnv / WrapperEnv classes running
+                         against a fake BulletClient (scripts/fake_bullet.py) whose physics backend is oracle/rbd.py.
+"""
+import argparse
+import base64
+import io
+import json
+import os
+import pickle
+import sys
+import types
+import zipfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def install_shims():
+    """Stub the third-party modules the reference imports but this container lacks."""
+    from oracle import xform as xf
+
+    tr = types.ModuleType("pybullet_utils.transformations")
+    tr.quaternion_multiply = lambda a, b: xf.quaternion_multiply(np.asarray(a, float), np.asarray(b, float))
+    tr.quaternion_conjugate = lambda q: xf.quaternion_conjugate(np.asarray(q, float))
+    tr.quaternion_inverse = lambda q: xf.quaternion_inverse(np.asarray(q, float))
+    tr.quaternion_about_axis = lambda a, ax: xf.quaternion_about_axis(float(a), np.asarray(ax, float))
+    tr.quaternion_from_euler = lambda r, p, y: xf.quaternion_from_euler(float(r), float(p), float(y))
+    tr.quaternion_slerp = lambda a, b, f: xf.quaternion_slerp(np.asarray(a, float), np.asarray(b, float), float(f))
+    pu = types.ModuleType("pybullet_utils")
+    pu.transformations = tr
+    sys.modules["pybullet_utils"] = pu
+    sys.modules["pybullet_utils.transformations"] = tr
+
+
+def motion_clips(ref):
+    mdir = os.path.join(ref, "OpenRoboRL/envs/quadruped_robot/task/motions")
+    out = {}
+    for fn in sorted(os.listdir(mdir)):
+        if not fn.endswith(".txt"):
+            continue
+        mj = json.load(open(os.path.join(mdir, fn)))
+        name = fn[:-4]
+        out[name + "/frames"] = np.array(mj["Frames"], dtype=np.float64)
+        out[name + "/meta"] = np.array([float(mj["FrameDuration"]), float(mj["LoopMode"] == "Wrap"),
+                                        float(bool(mj.get("EnableCycleOffsetPosition", False))),
+                                        float(bool(mj.get("EnableCycleOffsetRotation", False)))])
+    np.savez_compressed(os.path.join(GOLD, "motion_clips.npz"), **out)
+    print("motion_clips.npz:", sorted({k.split("/")[0] for k in out}))
+
+
+class _BoxStub(object):
+    def __setstate__(self, st):
+        self.__dict__.update(st)
+
+
+class _Unpickler(pickle.Unpickler):
+    def find_class(self, module, name):
+        if module.startswith("gym"):
+            return _BoxStub
+        return super().find_class(module, name)
+
+
+def policies(ref):
+    pdir = os.path.join(ref, "OpenRoboRL/envs/quadruped_robot/task/policies")
+    for name in ("laikago_pace", "minicheetah_trot"):
+        z = zipfile.ZipFile(os.path.join(pdir, name + ".zip"))
+        p = np.load(io.BytesIO(z.read("parameters")))
+        data = json.loads(z.read("data"))
+        out = {k: p["model/%s:0" % k] for k in ("pi_fc0/w", "pi_fc0/b", "pi_fc1/w", "pi_fc1/b", "pi/w", "pi/b")}
+        try:
+            box = _Unpickler(io.BytesIO(base64.b64decode(data["observation_space"][":serialized:"]))).load()
+            out["obs_low"], out["obs_high"] = np.asarray(box.low), np.asarray(box.high)
+        except Exception as exc:   # keep going: the bounds are an extra pin, not required
+            print("  (observation_space of %s not decoded: %r)" % (name, exc))
+        np.savez_compressed(os.path.join(GOLD, "policy_%s.npz" % name), **{k.replace("/", "_"): v for k, v in out.items()})
+        print("policy_%s.npz" % name, sorted(out))
+
+
+def motion_kat(ref):
+    """Known answers from the reference's own motion_data / pose3d / action_filter / minitaur_motor."""
+    sys.path.insert(0, os.path.join(ref, "OpenRoboRL"))
+    import collections
+    import collections.abc
+    collections.Sequence = collections.abc.Sequence      # removed in py3.10; minitaur_motor.py:61 uses it
+    from envs.quadruped_robot.task import motion_data
+    from envs.utilities import pose3d
+    from envs.utilities import action_filter
+    from envs.quadruped_robot.robots import minitaur_motor
+    mdir = os.path.join(ref, "OpenRoboRL/envs/quadruped_robot/task/motions")
+    out = {}
+    rng = np.random.RandomState(1234)
+    for name in ("laikago_pace", "laikago_spin", "laikago_hopturn", "minicheetah_trot"):
+        m = motion_data.MotionData(os.path.join(mdir, name + ".txt"))
+        dur = m.get_duration()
+        times = np.concatenate([[0.0, 0.033, 0.5, 0.7, 1.2345, -0.1, dur, 2 * dur, dur - 1e-9],
+                                rng.uniform(-0.3, 25.0, size=200)])
+        rec = dict(times=times, frames=m.get_frames(), vels=m._frame_vels, duration=dur,
+                   delta_pos=m._cycle_delta_pos, delta_heading=m._cycle_delta_heading)
+        f0s, f1s, bl, cyc, poses, vels, phases = [], [], [], [], [], [], []
+        for t in times:
+            f0, f1, b = m.calc_blend_idx(t)
+            f0s.append(f0); f1s.append(f1); bl.append(b); cyc.append(m.calc_cycle_count(t))
+            poses.append(m.calc_frame(t)); vels.append(m.calc_frame_vel(t)); phases.append(m.calc_phase(t))
+        rec.update(f0=np.array(f0s), f1=np.array(f1s), blend=np.array(bl), cycle=np.array(cyc), pose=np.array(poses),
+                   vel=np.array(vels), phase=np.array(phases))
+        for k, v in rec.items():
+            out["%s/%s" % (name, k)] = np.asarray(v)
+    # pose3d helpers on random unit quaternions
+    q = rng.normal(size=(64, 4)); q /= np.linalg.norm(q, axis=1, keepdims=True)
+    pts = rng.normal(size=(64, 3))
+    out["pose3d/q"] = q; out["pose3d/pts"] = pts
+    out["pose3d/heading"] = np.array([pose3d.calc_heading(x) for x in q])
+    out["pose3d/rotate"] = np.array([pose3d.QuaternionRotatePoint(p, x) for p, x in zip(pts, q)])
+    aa = [pose3d.QuaternionToAxisAngle(x) for x in q]
+    out["pose3d/axis"] = np.array([a[0] for a in aa]); out["pose3d/angle"] = np.array([a[1] for a in aa])
+    ang = rng.uniform(-10, 10, size=64)
+    out["pose3d/ang_in"] = ang
+    out["pose3d/norm_angle"] = np.array([pose3d.normalize_rotation_angle(a) for a in ang])
+    out["pose3d/map_pi"] = np.array(pose3d.MapToMinusPiToPi(list(ang)))
+    out["pose3d/heading_rot"] = np.array([pose3d.calc_heading_rot(x) for x in q])
+    # Butterworth action filter
+    f = action_filter.ActionFilterButter(sampling_rate=1 / (0.001 * 33), num_joints=12)
+    out["filter/b"] = f.b[0]; out["filter/a"] = f.a[0]
+    x0 = np.array([0, 0.67, -1.25] * 4)
+    f.init_history(x0)
+    xs = x0 + rng.normal(scale=0.2, size=(20, 12))
+    out["filter/x0"] = x0; out["filter/x"] = xs
+    out["filter/y"] = np.array([f.filter(x) for x in xs])
+    # PD motor model
+    mm = minitaur_motor.MotorModel(kp=[220.0] * 12, kd=[0.3, 2.0, 2.0] * 4, torque_limits=None)
+    qq, qd, cmd = rng.normal(size=(8, 12)), rng.normal(size=(8, 12)), rng.normal(size=(8, 12))
+    out["motor/q"], out["motor/qd"], out["motor/cmd"] = qq, qd, cmd
+    out["motor/tau"] = np.array([mm.convert_to_torque(c, a, b, b, minitaur_motor.POSITION)[0] for a, b, c in zip(qq, qd, cmd)])
+    np.savez_compressed(os.path.join(GOLD, "ref_motion_kat.npz"), **out)
+    print("ref_motion_kat.npz:", len(out), "arrays")
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--reference", default="/root/reference")
+    ap.add_argument("--skip-trace", action="store_true")
+    args = ap.parse_args()
+    os.makedirs(GOLD, exist_ok=True)
+    install_shims()
+    motion_clips(args.reference)
+    policies(args.reference)
+    motion_kat(args.reference)
+    if not args.skip_trace:
+        try:
+            from scripts import make_trace
+        except ImportError:
+            import make_trace
+        make_trace.main(args.reference, GOLD)
