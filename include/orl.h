@@ -210,6 +210,9 @@ int orl_forward_dynamics(orl_env* env, const float* pose_dev, const float* vel_d
 int orl_reward_terms(orl_env* env, float* terms_dev, void* stream);
 /* Number of kernels this handle has launched since creation (bench.py "gpu_launches"). */
 int64_t orl_launch_count(const orl_env* env);
+/* Measurement helper (no reference counterpart): sustained FP32 FFMA throughput of `device` in TFLOP/s,
+ * the denominator of the FP32-pipe roofline (the driver measures no FP32 figure). */
+int orl_fp32_peak(int32_t device, int32_t repeats, double* tflops_out);
 
 #ifdef __cplusplus
 }

@@ -98,6 +98,7 @@ SYMBOLS = {
     "orl_forward_dynamics": (C.c_int, [_P, _P, _P, _P, C.c_int32, _P, _P]),
     "orl_reward_terms": (C.c_int, [_P, _P, _P]),
     "orl_launch_count": (C.c_int64, [_P]),
+    "orl_fp32_peak": (C.c_int, [C.c_int32, C.c_int32, _P]),
 }
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libopenroborl_b200.so")

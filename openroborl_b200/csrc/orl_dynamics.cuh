@@ -206,7 +206,7 @@ ORL_DI void leg_dynamics(const orl_leg_model& L, const orl_robot_model& Mo, cons
         else f[2] = f[2] - fe;
         // Jacobian columns of the contact-point velocity: base w (3), base v (3), joints 0..kb
         float3 J[9];
-        J[0] = v3(0.f, r.z, -r.y); J[1] = v3(-r.z, 0.f, r.x); J[2] = v3(r.y, -r.x, 0.f);   // e_a x r
+        J[0] = v3(0.f, -r.z, r.y); J[1] = v3(r.z, 0.f, -r.x); J[2] = v3(-r.y, r.x, 0.f);   // e_a x r
         J[3] = v3(1.f, 0.f, 0.f); J[4] = v3(0.f, 1.f, 0.f); J[5] = v3(0.f, 0.f, 1.f);
 #pragma unroll
         for (int j = 0; j < 3; ++j) J[6 + j] = (j <= kb) ? cross(S[j].a, r - K.p[j]) : v3(0.f, 0.f, 0.f);

@@ -486,3 +486,46 @@ extern "C" int orl_reward_terms(orl_env* e, float* terms_dev, void* stream) {
   orl_reward_terms_kernel<<<(n * 4 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(e->dev, terms_dev);
   return check_launch(e, "orl_reward_terms_kernel");
 }
+
+// ---- FP32 FFMA micro-benchmark (roofline denominator) -------------------------------------------------
+__global__ void __launch_bounds__(256) orl_ffma_kernel(float* out, int iters, float a, float b) {
+  float x[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) x[i] = (float)(threadIdx.x + i) * 1e-3f;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) x[i] = fmaf(x[i], a, b);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += x[i];
+  if (s == 123.456f) out[blockIdx.x * blockDim.x + threadIdx.x] = s;   // never true; keeps the chain alive
+}
+
+extern "C" int orl_fp32_peak(int32_t device, int32_t repeats, double* tflops_out) {
+  if (!tflops_out) return ORL_ERR_INVALID;
+  if (cudaSetDevice(device) != cudaSuccess) return ORL_ERR_CUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return ORL_ERR_CUDA;
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+  float* d = nullptr;
+  if (cudaMalloc(&d, (size_t)blocks * threads * sizeof(float)) != cudaSuccess) return ORL_ERR_CUDA;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  double best = 0.0;
+  for (int r = 0; r < repeats + 1; ++r) {
+    cudaEventRecord(e0);
+    orl_ffma_kernel<<<blocks, threads>>>(d, iters, 0.999f, 1e-4f);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double tf = 2.0 * 16.0 * iters * (double)blocks * threads / (ms * 1e-3) / 1e12;
+    if (r > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(d);
+  if (cudaGetLastError() != cudaSuccess) return ORL_ERR_CUDA;
+  *tflops_out = best;
+  return ORL_OK;
+}

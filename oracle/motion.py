@@ -34,8 +34,11 @@ def postprocess_frames(frames):
         start = frames[0, :2].copy()
         frames[:, 0] -= start[0]
         frames[:, 1] -= start[1]
-        q = xf.QuaternionNormalize(frames[:, 3:7])
-        frames[:, 3:7] = xf.standardize_quaternion(q)
+        for f in range(frames.shape[0]):
+            # per-row np.linalg.norm of the 1-D quaternion, exactly as pose3d.QuaternionNormalize does
+            # (its dot-product summation order differs from a batched axis reduction by 1 ulp)
+            q = frames[f, 3:7] / np.linalg.norm(frames[f, 3:7])
+            frames[f, 3:7] = xf.standardize_quaternion(q)
     return frames
 
 

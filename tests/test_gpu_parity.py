@@ -1,0 +1,327 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the reference's golden vectors.
+
+Tolerances (north_star): motion-frame indices and termination flags bit-exact; FK and reward terms
+<= 1e-5 relative; mass matrix / inverse dynamics <= 1e-4 relative.  Full control steps (33 FP32 substeps
+with contact) are compared with the tolerances stated in each test.
+"""
+import numpy as np
+import pytest
+import torch
+
+from tests import common
+
+pytestmark = pytest.mark.gpu
+
+KAT = np.load(common.GOLD + "/ref_motion_kat.npz")
+PERM = [3, 4, 5, 0, 1, 2] + list(range(6, 18))      # interface [lin, ang, q] <- oracle [ang, lin, q]
+
+
+@pytest.fixture(scope="module")
+def laikago():
+    env = common.make_product("laikago", ["laikago_pace"], 256, seed=5)
+    orc = common.make_oracle("laikago", ["laikago_pace"], 256, seed=5, phys=common.oracle_phys_from_product(env.phys))
+    yield env, orc
+    env.close()
+
+
+@pytest.fixture(scope="module")
+def cheetah():
+    env = common.make_product("mini_cheetah", ["minicheetah_trot"], 128, seed=9)
+    orc = common.make_oracle("mini_cheetah", ["minicheetah_trot"], 128, seed=9, phys=common.oracle_phys_from_product(env.phys))
+    yield env, orc
+    env.close()
+
+
+# ---- (a1-a4) motion tables and frame lookup ---------------------------------------------------------
+@pytest.mark.parametrize("name", ["laikago_pace", "laikago_spin", "laikago_hopturn", "minicheetah_trot"])
+def test_motion_lookup_against_reference_golden(name):
+    robot = "mini_cheetah" if name.startswith("mini") else "laikago"
+    env = common.make_product(robot, [name], 8)
+    mt = env.motion_tables()
+    np.testing.assert_allclose(mt["frames"], KAT[name + "/frames"], rtol=0, atol=3e-16)    # host post-processing (f64)
+    np.testing.assert_allclose(mt["vels"], KAT[name + "/vels"], rtol=0, atol=1e-11)
+    assert mt["duration"][0] == float(KAT[name + "/duration"])
+    np.testing.assert_allclose(mt["delta_heading"][0], KAT[name + "/delta_heading"], atol=1e-14)
+    t = KAT[name + "/times"]
+    lk = env.motion_lookup(np.zeros(len(t), dtype=np.int32), t)
+    assert np.array_equal(lk["f0"], KAT[name + "/f0"]) and np.array_equal(lk["f1"], KAT[name + "/f1"])   # bit exact
+    assert np.array_equal(lk["cycle"], KAT[name + "/cycle"])
+    assert np.array_equal(lk["blend"], KAT[name + "/blend"])                                         # FP64, same op order
+    scale = np.abs(KAT[name + "/pose"]).max()
+    assert np.abs(lk["pose"] - KAT[name + "/pose"]).max() <= 1e-6 * max(scale, 1.0)
+    assert np.abs(lk["vel"] - KAT[name + "/vel"]).max() <= 1e-6 * np.abs(KAT[name + "/vel"]).max()
+    env.close()
+
+
+def test_motion_lookup_library_random_times():
+    names = ["laikago_pace", "laikago_trot", "laikago_spin", "laikago_hopturn", "laikago_sidesteps"]
+    env = common.make_product("laikago", names, 8)
+    orc = common.make_oracle("laikago", names, 8)
+    rng = np.random.default_rng(3)
+    clip = rng.integers(0, 5, size=20000)
+    t = rng.uniform(-0.3, 30.0, size=20000)
+    lk = env.motion_lookup(clip, t)
+    f0, f1, bl = orc.lib.calc_blend_idx(clip, t)
+    assert np.array_equal(lk["f0"], f0) and np.array_equal(lk["f1"], f1) and np.array_equal(lk["blend"], bl)
+    assert np.array_equal(lk["cycle"], orc.lib.calc_cycle_count(clip, t))
+    pose = orc.lib.calc_frame(clip, t)
+    assert np.abs(lk["pose"] - pose).max() <= 1e-6 * np.abs(pose).max()
+    env.close()
+
+
+# ---- (a8, a14) kinematics and dynamics ------------------------------------------------------------------
+@pytest.mark.parametrize("which", ["laikago", "cheetah"])
+def test_fk_mass_matrix_inverse_dynamics(which, request):
+    env, orc = request.getfixturevalue(which)
+    rng = np.random.default_rng(1)
+    n = 200
+    pose, vel = common.random_states(rng, n)
+    p64, v64 = pose.astype(np.float64), vel.astype(np.float64)
+    com = orc.tree.link_com(p64[:, 0:3], p64[:, 3:7], p64[:, 7:])
+    rel = (com - p64[:, None, 0:3])                                  # positions relative to the base
+    got = env.fk(pose) - pose[:, None, 0:3]
+    assert np.abs(got - rel).max() <= 1e-5 * np.abs(rel).max()       # FK <= 1e-5 relative
+    M_o = orc.tree.mass_matrix(p64[:, 0:3], p64[:, 3:7], p64[:, 7:])[:, PERM][:, :, PERM]
+    M = env.mass_matrix(pose)
+    assert np.abs(M - M_o).max() <= 1e-4 * np.abs(M_o).max()         # <= 1e-4 relative (measured ~1e-7)
+    assert np.abs(M - M.transpose(0, 2, 1)).max() == 0.0
+    acc = (rng.normal(size=(n, 18)) * 5).astype(np.float32)
+    nu = np.concatenate([v64[:, 3:6], v64[:, 0:3], v64[:, 6:]], axis=1)
+    nud = np.concatenate([acc[:, 3:6], acc[:, 0:3], acc[:, 6:]], axis=1).astype(np.float64)
+    tau_o = orc.tree.inverse_dynamics(p64[:, 0:3], p64[:, 3:7], p64[:, 7:], nu, nud)[:, PERM]
+    tau = env.inverse_dynamics(pose, vel, acc)
+    assert np.abs(tau - tau_o).max() <= 1e-4 * np.abs(tau_o).max()
+    # linearity in the acceleration: ID(a1 + a2) - ID(0) == (ID(a1) - ID(0)) + (ID(a2) - ID(0))
+    z = np.zeros_like(acc)
+    t0, t1, t2 = env.inverse_dynamics(pose, vel, z), env.inverse_dynamics(pose, vel, acc), env.inverse_dynamics(pose, vel, -acc)
+    assert np.abs((t1 - t0) + (t2 - t0)).max() <= 2e-3 * np.abs(t1).max()
+
+
+@pytest.mark.parametrize("which", ["laikago", "cheetah"])
+def test_forward_dynamics_with_contact(which, request):
+    env, orc = request.getfixturevalue(which)
+    rng = np.random.default_rng(2)
+    n = orc.N
+    pose, vel = common.random_states(rng, n)
+    pose[:, 2] = rng.uniform(0.15, 0.5, size=n)
+    pose[:, 3:7] = np.array(env.model.spec.INIT_QUAT) + rng.normal(size=(n, 4)) * 0.1
+    pose[:, 3:7] /= np.linalg.norm(pose[:, 3:7], axis=1, keepdims=True)
+    tau = (rng.normal(size=(n, 12)) * 5).astype(np.float32)
+    orc.pos, orc.quat, orc.q = [pose[:, a:b].astype(np.float64) for a, b in ((0, 3), (3, 7), (7, 19))]
+    orc.lin, orc.ang, orc.qd = [vel[:, a:b].astype(np.float64) for a, b in ((0, 3), (3, 6), (6, 18))]
+    acc_o = orc.forward_dynamics(tau.astype(np.float64))[:, PERM]
+    acc = env.forward_dynamics(pose, vel, tau)
+    # stiff contact (kn = 1e5) amplifies FP32 rounding of the penetration depth: 1e-4 of the batch scale
+    assert np.abs(acc - acc_o).max() <= 1e-4 * np.abs(acc_o).max()
+    # free fall: no contact, no torque, no velocity -> the base accelerates with gravity, bit for bit finite
+    pose[:, 2] = 5.0
+    ff = env.forward_dynamics(pose, np.zeros_like(vel), np.zeros_like(tau))
+    np.testing.assert_allclose(ff[:, 0:3], np.tile([0, 0, -10.0], (n, 1)), atol=2e-4)
+
+
+# ---- (a5-a7, a16) reset --------------------------------------------------------------------------------
+@pytest.mark.parametrize("which", ["laikago", "cheetah"])
+def test_reset_matches_oracle(which, request):
+    env, orc = request.getfixturevalue(which)
+    obs = env.reset().cpu().numpy()
+    obs_o = orc.reset()
+    st = env.get_state()
+    assert np.array_equal(st["clip"], orc.clip) and np.array_equal(st["warmup"].astype(bool), orc.warmup)
+    assert np.array_equal(st["time_offset"], orc.time_offset) and np.array_equal(st["prev_phase"], orc.prev_phase)   # FP64 exact
+    assert orc.warmup.any() and (~orc.warmup).any()                    # both RSI and warm-up episodes are covered
+    for k in ("pos", "quat", "q", "lin", "ang", "qd", "ref_pose", "ref_vel", "origin_pos", "origin_rot"):
+        assert np.abs(st[k] - getattr(orc, k)).max() <= 2e-6 * max(1.0, np.abs(getattr(orc, k)).max()), k
+    assert np.abs(obs - obs_o).max() <= 2e-6 * np.abs(obs_o).max()
+    # quirk A.6.1: the first observation shows the DEFAULT pose in the sensor histories
+    assert np.array_equal(obs[:, 0:12], np.zeros_like(obs[:, 0:12])) and np.array_equal(obs[:, 12:48], np.zeros_like(obs[:, 12:48]))
+    # perfect tracking right after reset: reward terms all 1 (imitation_task.py:350-356)
+    assert np.abs(env.reward_terms() - 1.0).max() <= 1e-5
+
+
+def test_masked_reset_only_touches_masked_robots(laikago):
+    env, _ = laikago
+    env.reset()
+    before = env.get_state()
+    mask = torch.zeros(env.num_robot, dtype=torch.uint8, device=env.device)
+    mask[::3] = 1
+    env.reset(mask)
+    after = env.get_state()
+    m = mask.cpu().numpy().astype(bool)
+    for k in before:
+        assert np.array_equal(before[k][~m], after[k][~m]), k
+    assert np.array_equal(after["episode"][m], before["episode"][m] + 1)
+    assert not np.array_equal(after["time_offset"][m], before["time_offset"][m])
+
+
+# ---- (a9-a13, a15) full control steps ------------------------------------------------------------------
+@pytest.mark.parametrize("which", ["laikago", "cheetah"])
+def test_control_step_matches_oracle(which, request):
+    env, orc = request.getfixturevalue(which)
+    env.reset()
+    orc.reset()
+    rng = np.random.default_rng(4)
+    worst = dict(reward=0.0, obs=0.0)
+    for step in range(4):
+        common.sync_oracle_from_product(orc, env.get_state())
+        # reward terms on IDENTICAL states (no physics in between): <= 1e-5 relative
+        rt, rt_o = env.reward_terms(), orc.reward_terms()
+        assert np.abs(rt - rt_o).max() <= 1e-5 * np.abs(rt_o).max() + 1e-7
+        act = rng.normal(scale=0.2, size=(env.num_robot, 12)).astype(np.float32)
+        o, r, d = env.step(torch.as_tensor(act, device=env.device))
+        oo, ro, do = orc.step(act.astype(np.float64))
+        o, r, d = o.cpu().numpy(), r.cpu().numpy(), d.cpu().numpy().astype(bool)
+        st = env.get_state()
+        # termination flags: bit exact wherever the oracle is not within 1e-4 of a threshold
+        safe = (orc._term_margin > 1e-4) & (orc._fall_margin > 1e-5)
+        assert safe.mean() > 0.95 and np.array_equal(d[safe], do[safe])
+        assert np.array_equal(st["prev_phase"], orc.prev_phase)                      # FP64 clock, exact
+        assert np.array_equal(st["substep_counter"], orc.substep_counter)
+        # 33 FP32 substeps with stiff contact against the FP64 oracle: absolute tolerances, median far below
+        ok = np.abs(st["qd"] - orc.qd).max(axis=1) < 2e-2                            # a contact toggling on a knife edge is allowed to differ
+        assert ok.mean() > 0.97
+        assert np.abs(r - ro)[ok].max() <= 1e-4 and np.median(np.abs(r - ro)) <= 5e-6
+        assert np.abs(st["q"] - orc.q)[ok].max() <= 2e-4
+        assert np.abs(st["pos"] - orc.pos)[ok].max() <= 1e-4
+        assert np.abs(o - oo)[ok].max() <= 2e-2 and np.median(np.abs(o - oo)) <= 1e-5
+        for k in ("act_hist", "filt_x", "filt_y", "prev_filtered", "ref_vel"):
+            assert np.abs(st[k] - getattr(orc, k)).max() <= 2e-6 * max(1.0, np.abs(getattr(orc, k)).max()), k
+        worst["reward"] = max(worst["reward"], np.abs(r - ro)[ok].max())
+        worst["obs"] = max(worst["obs"], np.abs(o - oo)[ok].max())
+    print("worst errors over 4 steps:", worst)
+
+
+def test_time_limit_and_termination_thresholds(laikago):
+    env, orc = laikago
+    env.reset(); orc.reset()
+    st = env.get_state()
+    # push some robots over the root-distance / root-rotation thresholds, keep others just inside
+    st["pos"][0:8, 0] += 1.05
+    st["pos"][8:16, 0] += 0.90
+    s, c = np.sin(0.85), np.cos(0.85)      # 1.7 rad > pi/2 about z
+    rot = np.array([0, 0, s, c], dtype=np.float32)
+    from oracle import xform as xf
+    st["quat"][16:24] = xf.quaternion_multiply(rot, st["quat"][16:24]).astype(np.float32)
+    st["env_step_counter"][24:32] = 598
+    env.set_state(st)
+    common.sync_oracle_from_product(orc, env.get_state())
+    act = np.zeros((env.num_robot, 12), dtype=np.float32)
+    _, _, d = env.step(torch.as_tensor(act, device=env.device))
+    _, _, do = orc.step(act.astype(np.float64))
+    d = d.cpu().numpy().astype(bool)
+    safe = (orc._term_margin > 1e-4) & (orc._fall_margin > 1e-5)
+    assert np.array_equal(d[safe], do[safe])
+    assert d[0:8].all() and d[16:24].all()
+    assert not d[24:32].any() or do[24:32].any()
+    _, _, d2 = env.step(torch.as_tensor(act, device=env.device))       # env_step_counter reaches 600
+    assert d2.cpu().numpy()[24:32].all()
+
+
+# ---- size-independent properties at BASELINE.json's full size -------------------------------------------
+def test_full_size_properties():
+    N = 4096
+    env = common.make_product("laikago", ["laikago_pace"], N, seed=21)
+    obs0 = env.reset().clone()
+    assert np.abs(env.reward_terms() - 1.0).max() <= 1e-5                 # perfect tracking after reset
+    lo, hi = env.observation_bounds()
+    o = obs0.cpu().numpy()
+    assert np.isfinite(o).all() and (o >= lo - 1e-4).all() and (o <= hi + 1e-4).all()
+    gen = torch.Generator(device=env.device); gen.manual_seed(0)
+    acts = [torch.randn((N, 12), device=env.device, generator=gen) * 0.125 for _ in range(5)]
+    outs = []
+    for a in acts:
+        o, r, d = env.step(a)
+        outs.append((o.clone(), r.clone(), d.clone()))
+    r_all = torch.stack([x[1] for x in outs]).cpu().numpy()
+    assert np.isfinite(r_all).all() and r_all.min() >= 0.0 and r_all.max() <= 1.0 + 1e-6
+    # determinism: same seed, same actions -> identical bits
+    env2 = common.make_product("laikago", ["laikago_pace"], N, seed=21)
+    assert torch.equal(env2.reset(), obs0)
+    for a, (o1, r1, d1) in zip(acts, outs):
+        o2, r2, d2 = env2.step(a)
+        assert torch.equal(o2, o1) and torch.equal(r2, r1) and torch.equal(d2, d1)
+    # sharding independence: two half-size handles keyed by global ids reproduce the full batch
+    h0 = common.make_product("laikago", ["laikago_pace"], N // 2, seed=21, gid0=0)
+    h1 = common.make_product("laikago", ["laikago_pace"], N // 2, seed=21, gid0=N // 2)
+    assert torch.equal(torch.cat([h0.reset(), h1.reset()]), obs0)
+    oa, ra, _ = h0.step(acts[0][:N // 2].contiguous())
+    ob, rb, _ = h1.step(acts[0][N // 2:].contiguous())
+    assert torch.equal(torch.cat([oa, ob]), outs[0][0]) and torch.equal(torch.cat([ra, rb]), outs[0][1])
+    for e in (env, env2, h0, h1):
+        e.close()
+
+
+def test_host_buffer_api_equals_device_api_and_ragged_sizes():
+    for N in (1, 7, 9, 33):                      # ragged: not a multiple of the 8 robots a warp owns
+        a = common.make_product("laikago", ["laikago_pace"], N, seed=2)
+        b = common.make_product("laikago", ["laikago_pace"], N, seed=2)
+        assert np.array_equal(a.reset().cpu().numpy(), b.reset_host())
+        act = np.random.default_rng(N).normal(scale=0.1, size=(N, 12)).astype(np.float32)
+        o, r, d = a.step(torch.as_tensor(act, device=a.device))
+        oh, rh, dh = b.step_host(act)
+        assert np.array_equal(o.cpu().numpy(), oh) and np.array_equal(r.cpu().numpy(), rh) and np.array_equal(d.cpu().numpy(), dh)
+        # a batch is a prefix of a larger batch with the same seed (per-robot RNG keyed by global id)
+        big = common.make_product("laikago", ["laikago_pace"], 40, seed=2)
+        assert np.array_equal(big.reset_host()[:N], common.make_product("laikago", ["laikago_pace"], N, seed=2).reset_host())
+        a.close(); b.close(); big.close()
+
+
+def test_auto_reset_and_statistics():
+    N = 512
+    env = common.make_product("laikago", ["laikago_pace"], N, seed=1, auto_reset=True, max_episode_steps=5)
+    env.reset()
+    env.stats(reset=True)
+    act = torch.zeros((N, 12), device=env.device)
+    tot_r = 0.0
+    for i in range(5):
+        o, r, d = env.step(act)
+        tot_r += float(r.double().sum())
+    assert d.cpu().numpy().all()                         # time limit after 5 steps
+    st = env.get_state()
+    assert (st["env_step_counter"] == 0).all() and (st["episode"] >= 2).all() and (st["ep_return"] == 0).all()
+    s = env.stats()
+    assert s[3] == 5 * N and abs(s[0] - tot_r) < 1e-3 * tot_r and s[2] >= N
+    # without auto reset the caller resets; done robots keep stepping (SURVEY.md 8b "episode semantics")
+    env2 = common.make_product("laikago", ["laikago_pace"], 16, seed=1, auto_reset=False, max_episode_steps=2)
+    env2.reset()
+    for i in range(3):
+        _, _, d = env2.step(torch.zeros((16, 12), device=env2.device))
+    assert d.cpu().numpy().all() and (env2.get_state()["env_step_counter"] == 3).all()
+    env.close(); env2.close()
+
+
+def test_errors_cross_the_boundary_as_python_exceptions():
+    with pytest.raises(ValueError, match="wrong robot select"):
+        common.make_product("spot", ["laikago_pace"], 4)
+    from openroborl_b200.env import BatchedImitationEnv
+    with pytest.raises(ValueError, match="No reference motions"):
+        BatchedImitationEnv("laikago", [], num_robot=4)
+    env = common.make_product("laikago", ["laikago_pace"], 4)
+    with pytest.raises(ValueError):
+        env.step(torch.zeros((3, 12), device=env.device))
+    with pytest.raises(ValueError):
+        env.set_max_episode_steps(0)
+    env.close()
+
+
+def test_policy_rollout_statistics():
+    """Pretrained reference policy (golden actor MLP) as the action source, 64 robots, 40 steps.
+
+    Trajectories are chaotic, so the FP32 kernel and the FP64 oracle are compared by episode statistics
+    (north_star: "contact rollouts ... by episode-reward statistics"): mean reward within 0.02.
+    """
+    N = 64
+    policy = common.load_policy("laikago_pace")
+    env = common.make_product("laikago", ["laikago_pace"], N, seed=8)
+    orc = common.make_oracle("laikago", ["laikago_pace"], N, seed=8, phys=common.oracle_phys_from_product(env.phys))
+    o = env.reset().cpu().numpy()
+    oo = orc.reset()
+    rs, ros = [], []
+    for t in range(40):
+        _, r, _ = env.step(torch.as_tensor(policy(o), device=env.device))
+        o = env.obs.cpu().numpy()
+        oo, ro, _ = orc.step(policy(oo).astype(np.float64))
+        rs.append(r.cpu().numpy()); ros.append(ro)
+    rs, ros = np.array(rs), np.array(ros)
+    assert np.abs(rs[:5] - ros[:5]).max() < 5e-3            # short horizon: still the same trajectory
+    assert abs(rs.mean() - ros.mean()) < 0.02
+    env.close()
