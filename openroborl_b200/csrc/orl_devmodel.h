@@ -1,0 +1,38 @@
+// Device-side packed copy of orl_robot_model: float4-aligned so that a lane fetches its leg's constants
+// with LDS.128 from shared memory, contact points grouped per body with a bounding radius for culling.
+// Built on the host by pack_model() (orl_env.cu) at orl_create time.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/orl.h"
+
+struct __align__(16) DevJoint {
+  float4 r0, r1, r2;   // R_fix rows (xyz) + p_fix component (w)
+  float4 i0;           // Ixx Ixy Ixz Iyy        (about the COM, body frame)
+  float4 i1;           // Iyz Izz mass com.x
+  float4 c1;           // com.y com.z lower upper
+  float4 m0;           // damping dir offset kp
+  float4 m1;           // kd init_angle motor(int bits) bounding radius of this body's collision points
+};
+struct __align__(16) DevCp {
+  float4 a;            // local xyz, radius
+  float4 b;            // mu, margin, is_foot (int bits), unused
+};
+struct __align__(16) DevLeg {
+  DevJoint j[3];
+  float4 ee[2];        // end-effector link COM xyz, body (int bits)
+  int4 meta;           // n_ee, base bounding radius (float bits), max margin of non-foot points (float bits), unused
+  int4 cnt;            // collision points on body 0, 1, 2 and on the base share; stored in that order in cp[]
+  DevCp cp[ORL_MAX_CP];
+};
+struct __align__(16) DevModel {
+  float4 b0;           // base mass, Ixx, Ixy, Ixz
+  float4 b1;           // Iyy, Iyz, Izz, max_angle_change
+  float4 ipos;         // init position
+  float4 iquat;        // init orientation
+  DevLeg leg[ORL_NUM_LEGS];
+  int32_t n_links, pad0, pad1, pad2;
+  int32_t link_leg[ORL_MAX_LINKS];
+  int32_t link_body[ORL_MAX_LINKS];
+  float4 link_com[ORL_MAX_LINKS];
+};

@@ -10,14 +10,18 @@
 // 6x6 LDL^T.  Ground contact is a semi-implicit penalty model: the force at the start-of-substep
 // velocity enters RNEA as an external force and its velocity derivative (frozen diagonal D) adds
 // dt * J^T D J to the same block pattern.
+//
+// v2 (profiles/r01_v1_step_kernel.md): model constants come as float4 from shared memory, collision
+// points are culled per body with a bounding radius and a warp vote, trigonometry / reciprocals inside
+// the substep loop use the SFU, and every sum of products is written as an FMA chain.
 #pragma once
 #include "orl_math.cuh"
-#include "../../include/orl.h"
+#include "orl_devmodel.h"
 
 struct PhysParams {
   float dt, g;              // g = -gravity_z (>0)
-  float kn, bn, d0, bt;
-  float klim, dlim, e0;
+  float kn, bn, inv_d0, bt;
+  float klim, dlim, inv_e0;
 };
 
 // rigid-body inertia at the frame-A origin: mass, first moment h = m c, rotational inertia about the origin
@@ -26,19 +30,37 @@ ORL_DI RBI operator+(const RBI& a, const RBI& b) { RBI o; o.m = a.m + b.m; o.h =
 struct SV { float3 a, l; };   // spatial vector: angular, linear
 ORL_DI SV operator+(const SV& x, const SV& y) { SV o; o.a = x.a + y.a; o.l = x.l + y.l; return o; }
 ORL_DI SV operator-(const SV& x, const SV& y) { SV o; o.a = x.a - y.a; o.l = x.l - y.l; return o; }
-ORL_DI float sdot(const SV& x, const SV& y) { return dot(x.a, y.a) + dot(x.l, y.l); }
+ORL_DI float sdot(const SV& x, const SV& y) {
+  return fmaf(x.a.x, y.a.x, fmaf(x.a.y, y.a.y, fmaf(x.a.z, y.a.z, fmaf(x.l.x, y.l.x, fmaf(x.l.y, y.l.y, x.l.z * y.l.z)))));
+}
 // I * [w; v] = [I w + h x v ; m v - h x w]
-ORL_DI SV apply(const RBI& B, const SV& v) { SV o; o.a = mul(B.I, v.a) + cross(B.h, v.l); o.l = B.m * v.l - cross(B.h, v.a); return o; }
-// motion cross product  v x m
-ORL_DI SV crm(const SV& v, const SV& m) { SV o; o.a = cross(v.a, m.a); o.l = cross(v.a, m.l) + cross(v.l, m.a); return o; }
-// force cross product  v x* f
-ORL_DI SV crf(const SV& v, const SV& f) { SV o; o.a = cross(v.a, f.a) + cross(v.l, f.l); o.l = cross(v.a, f.l); return o; }
+ORL_DI SV apply(const RBI& B, const SV& v) {
+  SV o;
+  o.a = cross_add(B.h, v.l, mul(B.I, v.a));
+  o.l = cross_add(v.a, B.h, B.m * v.l);
+  return o;
+}
+// acc + v x m   (motion cross product)
+ORL_DI SV crm_add(const SV& v, const SV& m, const SV& acc) {
+  SV o;
+  o.a = cross_add(v.a, m.a, acc.a);
+  o.l = cross_add(v.l, m.a, cross_add(v.a, m.l, acc.l));
+  return o;
+}
+// acc + v x* f  (force cross product)
+ORL_DI SV crf_add(const SV& v, const SV& f, const SV& acc) {
+  SV o;
+  o.a = cross_add(v.l, f.l, cross_add(v.a, f.a, acc.a));
+  o.l = cross_add(v.a, f.l, acc.l);
+  return o;
+}
 
 ORL_DI RBI body_inertia(float m, float3 c /* COM rel. origin, frame A */, const S3& Ic /* about COM, frame A */) {
   RBI o; o.m = m; o.h = m * c;
-  const float cc = dot(c, c);
-  o.I.xx = Ic.xx + m * (cc - c.x * c.x); o.I.yy = Ic.yy + m * (cc - c.y * c.y); o.I.zz = Ic.zz + m * (cc - c.z * c.z);
-  o.I.xy = Ic.xy - m * c.x * c.y; o.I.xz = Ic.xz - m * c.x * c.z; o.I.yz = Ic.yz - m * c.y * c.z;
+  const float mcc = m * dot(c, c);
+  const float3 mc = o.h;
+  o.I.xx = fmaf(-mc.x, c.x, Ic.xx + mcc); o.I.yy = fmaf(-mc.y, c.y, Ic.yy + mcc); o.I.zz = fmaf(-mc.z, c.z, Ic.zz + mcc);
+  o.I.xy = fmaf(-mc.x, c.y, Ic.xy); o.I.xz = fmaf(-mc.x, c.z, Ic.xz); o.I.yz = fmaf(-mc.y, c.z, Ic.yz);
   return o;
 }
 
@@ -57,71 +79,74 @@ ORL_DI void rbi_to_tri(const RBI& B, float A[21]) {
 
 // LDL^T solve of a symmetric positive definite 6x6 (lower triangle in A, destroyed); x overwrites b
 ORL_DI void ldl6_solve(float A[21], float b[6]) {
-  float D[6];
+  float D[6], Dinv[6];
 #pragma unroll
   for (int j = 0; j < 6; ++j) {
     float d = A[TRI(j, j)];
 #pragma unroll
-    for (int k = 0; k < j; ++k) d -= A[TRI(j, k)] * A[TRI(j, k)] * D[k];
+    for (int k = 0; k < j; ++k) d = fmaf(-A[TRI(j, k)] * D[k], A[TRI(j, k)], d);
     D[j] = d;
-    const float inv = 1.0f / d;
+    Dinv[j] = fast_rcp(d);
 #pragma unroll
     for (int i = j + 1; i < 6; ++i) {
       float s = A[TRI(i, j)];
 #pragma unroll
-      for (int k = 0; k < j; ++k) s -= A[TRI(i, k)] * A[TRI(j, k)] * D[k];
-      A[TRI(i, j)] = s * inv;
+      for (int k = 0; k < j; ++k) s = fmaf(-A[TRI(i, k)] * D[k], A[TRI(j, k)], s);
+      A[TRI(i, j)] = s * Dinv[j];
     }
   }
 #pragma unroll
   for (int i = 1; i < 6; ++i)
 #pragma unroll
-    for (int k = 0; k < i; ++k) b[i] -= A[TRI(i, k)] * b[k];
+    for (int k = 0; k < i; ++k) b[i] = fmaf(-A[TRI(i, k)], b[k], b[i]);
 #pragma unroll
-  for (int i = 0; i < 6; ++i) b[i] /= D[i];
+  for (int i = 0; i < 6; ++i) b[i] *= Dinv[i];
 #pragma unroll
   for (int i = 4; i >= 0; --i)
 #pragma unroll
-    for (int k = i + 1; k < 6; ++k) b[i] -= A[TRI(k, i)] * b[k];
+    for (int k = i + 1; k < 6; ++k) b[i] = fmaf(-A[TRI(k, i)], b[k], b[i]);
 }
 
 // LDL^T of a symmetric positive definite 3x3: A = [a00 a10 a11 a20 a21 a22] (lower, row-major)
 struct LDL3 { float l10, l20, l21, i0, i1, i2; };
 ORL_DI LDL3 ldl3(const float A[6]) {
   LDL3 f;
-  f.i0 = 1.0f / A[0];
+  f.i0 = fast_rcp(A[0]);
   f.l10 = A[1] * f.i0; f.l20 = A[3] * f.i0;
-  const float d1 = A[2] - f.l10 * A[1];
-  f.i1 = 1.0f / d1;
-  const float t = A[4] - f.l20 * A[1];
+  const float d1 = fmaf(-f.l10, A[1], A[2]);
+  f.i1 = fast_rcp(d1);
+  const float t = fmaf(-f.l20, A[1], A[4]);
   f.l21 = t * f.i1;
-  const float d2 = A[5] - f.l20 * A[3] - f.l21 * t;
-  f.i2 = 1.0f / d2;
+  const float d2 = fmaf(-f.l21, t, fmaf(-f.l20, A[3], A[5]));
+  f.i2 = fast_rcp(d2);
   return f;
 }
 ORL_DI void ldl3_solve(const LDL3& f, float& x0, float& x1, float& x2) {
-  x1 -= f.l10 * x0; x2 -= f.l20 * x0 + f.l21 * x1;
+  x1 = fmaf(-f.l10, x0, x1); x2 = fmaf(-f.l21, x1, fmaf(-f.l20, x0, x2));
   x0 *= f.i0; x1 *= f.i1; x2 *= f.i2;
-  x1 -= f.l21 * x2; x0 -= f.l10 * x1 + f.l20 * x2;
+  x1 = fmaf(-f.l21, x2, x1); x0 = fmaf(-f.l20, x2, fmaf(-f.l10, x1, x0));
 }
 
-// forward kinematics of one leg in frame A
+ORL_DI float3 f4xyz(float4 v) { return v3(v.x, v.y, v.z); }
+
+// forward kinematics of one leg in frame A.  FAST: SFU sincos (abs. error < 4e-7 on [-pi, pi]).
 struct LegFK { M3 R[3]; float3 p[3]; };
-ORL_DI void leg_fk(const orl_leg_model& L, const M3& Rb, const float q[3], LegFK& K) {
+template <bool FAST>
+ORL_DI void leg_fk(const DevLeg& L, const M3& Rb, const float q[3], LegFK& K) {
   M3 Rp = Rb; float3 pp = v3(0.f, 0.f, 0.f);
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
-    M3 F;
-    F.r0 = v3(L.R_fix[k][0], L.R_fix[k][1], L.R_fix[k][2]);
-    F.r1 = v3(L.R_fix[k][3], L.R_fix[k][4], L.R_fix[k][5]);
-    F.r2 = v3(L.R_fix[k][6], L.R_fix[k][7], L.R_fix[k][8]);
+    const float4 a0 = L.j[k].r0, a1 = L.j[k].r1, a2 = L.j[k].r2;
+    M3 F; F.r0 = f4xyz(a0); F.r1 = f4xyz(a1); F.r2 = f4xyz(a2);
     float s, c;
-    sincosf(q[k], &s, &c);
-    K.p[k] = pp + mul(Rp, v3(L.p_fix[k][0], L.p_fix[k][1], L.p_fix[k][2]));
+    if (FAST) __sincosf(q[k], &s, &c); else sincosf(q[k], &s, &c);
+    K.p[k] = madd(Rp, v3(a0.w, a1.w, a2.w), pp);
     K.R[k] = mul_rz(mul(Rp, F), s, c);
     Rp = K.R[k]; pp = K.p[k];
   }
 }
+ORL_DI M3 pickR(const LegFK& K, int kb) { return kb == 0 ? K.R[0] : (kb == 1 ? K.R[1] : K.R[2]); }
+ORL_DI float3 pickp(const LegFK& K, int kb) { return kb == 0 ? K.p[0] : (kb == 1 ? K.p[1] : K.p[2]); }
 
 // What the caller can ask leg_dynamics to export (parity entry points)
 struct DynExport {
@@ -132,17 +157,84 @@ struct DynExport {
   float pb[6];         // base bias
 };
 
+// Accumulators of the contact model for one lane
+struct ContactAcc {
+  float Wbb[21], Wll[6];
+  SV Wbl[3];
+  SV fb_ext;
+  bool any;
+};
+
+// One active collision point: force at the old velocity -> external force on its body, frozen derivative -> W.
+// KB is the body the point is fixed to (-1 = base); r is the contact location relative to the frame-A origin.
+template <int KB>
+ORL_DI void contact_point(const PhysParams& P, float d, float mu, float3 r, const SV& vk, float3 e_cl, const SV S[3],
+                          const float3 p[3], SV f[3], ContactAcc& W) {
+  const float3 V = cross_add(vk.a, r, vk.l);
+  const float sc = fminf(1.0f, d * P.inv_d0);
+  const float fn = fmaxf(0.0f, fmaf(-P.bn * sc, V.z, P.kn * d));
+  const float vt2 = fmaf(V.x, V.x, V.y * V.y);
+  const float ct = fminf(P.bt, mu * fn * rsqrtf(fmaxf(vt2, 1e-18f)));
+  const float cn = fn > 0.f ? fmaf(P.bn, sc, P.kn * P.dt) : 0.f;
+  const float3 Dd = v3(P.dt * ct, P.dt * ct, P.dt * cn);
+  // force at the old velocity, corrected for the classical/spatial acceleration difference
+  const float3 F = v3(fmaf(-Dd.x, e_cl.x, -ct * V.x), fmaf(-Dd.y, e_cl.y, -ct * V.y), fmaf(-Dd.z, e_cl.z, fn));
+  SV fe; fe.a = cross(r, F); fe.l = F;
+  if (KB < 0) W.fb_ext = W.fb_ext + fe; else f[KB < 0 ? 0 : KB] = f[KB < 0 ? 0 : KB] - fe;
+  // Jacobian columns of the contact-point velocity: base w (e_a x r), base v (e_a), joints 0..KB
+  float3 J[9];
+  J[0] = v3(0.f, -r.z, r.y); J[1] = v3(r.z, 0.f, -r.x); J[2] = v3(-r.y, r.x, 0.f);
+  J[3] = v3(1.f, 0.f, 0.f); J[4] = v3(0.f, 1.f, 0.f); J[5] = v3(0.f, 0.f, 1.f);
+#pragma unroll
+  for (int j = 0; j < 3; ++j) J[6 + j] = (j <= KB) ? cross(S[j].a, r - p[j]) : v3(0.f, 0.f, 0.f);
+  float3 DJ[9];
+#pragma unroll
+  for (int a = 0; a < 9; ++a) DJ[a] = v3(Dd.x * J[a].x, Dd.y * J[a].y, Dd.z * J[a].z);
+#pragma unroll
+  for (int a = 0; a < 6; ++a)
+#pragma unroll
+    for (int b = 0; b <= a; ++b) W.Wbb[TRI(a, b)] += dot(DJ[a], J[b]);
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    if (j <= KB) {
+      W.Wbl[j].a += v3(dot(DJ[0], J[6 + j]), dot(DJ[1], J[6 + j]), dot(DJ[2], J[6 + j]));
+      W.Wbl[j].l += v3(dot(DJ[3], J[6 + j]), dot(DJ[4], J[6 + j]), dot(DJ[5], J[6 + j]));
+    }
+  }
+  if (KB >= 0) W.Wll[0] += dot(DJ[6], J[6]);
+  if (KB >= 1) { W.Wll[1] += dot(DJ[7], J[6]); W.Wll[2] += dot(DJ[7], J[7]); }
+  if (KB >= 2) { W.Wll[3] += dot(DJ[8], J[6]); W.Wll[4] += dot(DJ[8], J[7]); W.Wll[5] += dot(DJ[8], J[8]); }
+  W.any = true;
+}
+
+// All collision points of body KB of this lane: bounding-radius cull, warp vote, then per-point test.
+template <int KB>
+ORL_DI void contact_body(const DevLeg& L, const PhysParams& P, int first, int count, float brad, float base_z, const M3& Rk,
+                         float3 pk, const SV& vk, float3 e_cl, const SV S[3], const float3 p[3], SV f[3], ContactAcc& W) {
+  const float oz = base_z + pk.z;
+  if (!__any_sync(0xffffffffu, oz < brad)) return;       // warp-uniform skip: nobody's body KB is near the ground
+  if (oz >= brad) return;
+  for (int i = first; i < first + count; ++i) {
+    const float4 a = L.cp[i].a;
+    const float z = oz + dot(Rk.r2, f4xyz(a)) - a.w;
+    if (z < 0.f) {
+      float3 r = madd(Rk, f4xyz(a), pk); r.z -= a.w;
+      contact_point<KB>(P, -z, L.cp[i].b.x, r, vk, e_cl, S, p, f, W);
+    }
+  }
+}
+
 // One dynamics evaluation for this lane's leg.  Returns the spatial base acceleration (a_b: angular
 // alpha, linear a_lin so that d/dt v_com = a_lin + w x v) and this leg's joint accelerations.
 // tau: generalised joint forces in URDF joint space (motor + limit + damping torques).
-template <bool CONTACT, bool EXPORT>
-ORL_DI void leg_dynamics(const orl_leg_model& L, const orl_robot_model& Mo, const PhysParams& P, const M3& Rb,
-                         float base_z, float3 wb, float3 vb, const float q[3], const float qd[3], const float tau[3],
-                         float3& alpha_b, float3& alin_b, float qdd[3], DynExport* ex) {
+template <bool CONTACT, bool EXPORT, bool FAST>
+ORL_DI void leg_dynamics(const DevLeg& L, const DevModel& Mo, const PhysParams& P, const M3& Rb, float base_z, float3 wb,
+                         float3 vb, const float q[3], const float qd[3], const float tau[3], float3& alpha_b, float3& alin_b,
+                         float qdd[3], DynExport* ex) {
   LegFK K;
-  leg_fk(L, Rb, q, K);
+  leg_fk<FAST>(L, Rb, q, K);
   // ---- velocities, velocity-product accelerations, per-body inertia and bias force -------------
-  SV S[3], v[3], avp[3], f[3];
+  SV S[3], v[3], f[3];
   RBI I[3];
   SV vp; vp.a = wb; vp.l = vb;
   SV ap; ap.a = v3(0.f, 0.f, 0.f); ap.l = v3(0.f, 0.f, P.g);    // a0 = -a_gravity
@@ -151,82 +243,34 @@ ORL_DI void leg_dynamics(const orl_leg_model& L, const orl_robot_model& Mo, cons
     S[k].a = col(K.R[k], 2);
     S[k].l = cross(K.p[k], S[k].a);
     SV sq; sq.a = qd[k] * S[k].a; sq.l = qd[k] * S[k].l;
-    v[k] = vp + sq;
-    avp[k] = ap + crm(vp, sq);
-    const float3 c = K.p[k] + mul(K.R[k], v3(L.com[k][0], L.com[k][1], L.com[k][2]));
-    S3 Ic = {L.inertia[k][0], L.inertia[k][1], L.inertia[k][2], L.inertia[k][3], L.inertia[k][4], L.inertia[k][5]};
-    I[k] = body_inertia(L.mass[k], c, rot_sym(K.R[k], Ic));
-    f[k] = apply(I[k], avp[k]) + crf(v[k], apply(I[k], v[k]));
-    vp = v[k]; ap = avp[k];
+    v[k].a = vp.a + sq.a; v[k].l = vp.l + sq.l;
+    const SV avp = crm_add(vp, sq, ap);
+    const float4 i0 = L.j[k].i0, i1 = L.j[k].i1, c1 = L.j[k].c1;
+    const float3 c = madd(K.R[k], v3(i1.w, c1.x, c1.y), K.p[k]);
+    const S3 Ic = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y};
+    I[k] = body_inertia(i1.z, c, rot_sym(K.R[k], Ic));
+    f[k] = crf_add(v[k], apply(I[k], v[k]), apply(I[k], avp));
+    vp = v[k]; ap = avp;
   }
   // ---- contact: explicit force -> external force; implicit part -> W blocks --------------------
-  float Wbb[21], Wll[6];
-  SV Wbl[3];
-  SV fb_ext; fb_ext.a = v3(0.f, 0.f, 0.f); fb_ext.l = v3(0.f, 0.f, 0.f);
+  ContactAcc W;
+  W.any = false;
+  W.fb_ext.a = v3(0.f, 0.f, 0.f); W.fb_ext.l = v3(0.f, 0.f, 0.f);
 #pragma unroll
-  for (int i = 0; i < 21; ++i) Wbb[i] = 0.f;
+  for (int i = 0; i < 21; ++i) W.Wbb[i] = 0.f;
 #pragma unroll
-  for (int i = 0; i < 6; ++i) Wll[i] = 0.f;
+  for (int i = 0; i < 6; ++i) W.Wll[i] = 0.f;
 #pragma unroll
-  for (int k = 0; k < 3; ++k) { Wbl[k].a = v3(0.f, 0.f, 0.f); Wbl[k].l = v3(0.f, 0.f, 0.f); }
+  for (int k = 0; k < 3; ++k) { W.Wbl[k].a = v3(0.f, 0.f, 0.f); W.Wbl[k].l = v3(0.f, 0.f, 0.f); }
   if (CONTACT) {
     const float3 e_cl = cross(wb, vb);     // classical - spatial linear base acceleration
-    for (int i = 0; i < L.n_cp; ++i) {
-      const orl_contact_point& cp = L.cp[i];
-      const int kb = cp.body;
-      const float3 loc = v3(cp.local[0], cp.local[1], cp.local[2]);
-      float3 rz_row; float pz;
-      if (kb < 0) { rz_row = Rb.r2; pz = 0.f; }
-      else if (kb == 0) { rz_row = K.R[0].r2; pz = K.p[0].z; }
-      else if (kb == 1) { rz_row = K.R[1].r2; pz = K.p[1].z; }
-      else { rz_row = K.R[2].r2; pz = K.p[2].z; }
-      const float z = base_z + pz + dot(rz_row, loc) - cp.radius;
-      if (z < 0.f) {
-        M3 Rk; float3 pk; SV vk;
-        if (kb < 0) { Rk = Rb; pk = v3(0.f, 0.f, 0.f); vk.a = wb; vk.l = vb; }
-        else if (kb == 0) { Rk = K.R[0]; pk = K.p[0]; vk = v[0]; }
-        else if (kb == 1) { Rk = K.R[1]; pk = K.p[1]; vk = v[1]; }
-        else { Rk = K.R[2]; pk = K.p[2]; vk = v[2]; }
-        float3 r = pk + mul(Rk, loc); r.z -= cp.radius;            // contact location rel. frame-A origin
-        const float3 V = vk.l + cross(vk.a, r);
-        const float d = -z;
-        const float sc = fminf(1.0f, d / P.d0);
-        const float fn = fmaxf(0.0f, P.kn * d - P.bn * sc * V.z);
-        const float vt = sqrtf(V.x * V.x + V.y * V.y);
-        const float ct = fminf(P.bt, cp.mu * fn / fmaxf(vt, 1e-9f));
-        const float cn = fn > 0.f ? P.kn * P.dt + P.bn * sc : 0.f;
-        const float3 D = v3(ct, ct, cn);
-        // force at the old velocity, corrected for the classical/spatial acceleration difference
-        float3 F = v3(-ct * V.x, -ct * V.y, fn);
-        F = F - P.dt * v3(D.x * e_cl.x, D.y * e_cl.y, D.z * e_cl.z);
-        SV fe; fe.a = cross(r, F); fe.l = F;
-        if (kb < 0) fb_ext = fb_ext + fe;
-        else if (kb == 0) f[0] = f[0] - fe;
-        else if (kb == 1) f[1] = f[1] - fe;
-        else f[2] = f[2] - fe;
-        // Jacobian columns of the contact-point velocity: base w (3), base v (3), joints 0..kb
-        float3 J[9];
-        J[0] = v3(0.f, -r.z, r.y); J[1] = v3(r.z, 0.f, -r.x); J[2] = v3(-r.y, r.x, 0.f);   // e_a x r
-        J[3] = v3(1.f, 0.f, 0.f); J[4] = v3(0.f, 1.f, 0.f); J[5] = v3(0.f, 0.f, 1.f);
-#pragma unroll
-        for (int j = 0; j < 3; ++j) J[6 + j] = (j <= kb) ? cross(S[j].a, r - K.p[j]) : v3(0.f, 0.f, 0.f);
-        const float3 Dd = P.dt * D;
-        float3 DJ[9];
-#pragma unroll
-        for (int a = 0; a < 9; ++a) DJ[a] = v3(Dd.x * J[a].x, Dd.y * J[a].y, Dd.z * J[a].z);
-#pragma unroll
-        for (int a = 0; a < 6; ++a)
-#pragma unroll
-          for (int b = 0; b <= a; ++b) Wbb[TRI(a, b)] += dot(DJ[a], J[b]);
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          Wbl[j].a += v3(dot(DJ[0], J[6 + j]), dot(DJ[1], J[6 + j]), dot(DJ[2], J[6 + j]));
-          Wbl[j].l += v3(dot(DJ[3], J[6 + j]), dot(DJ[4], J[6 + j]), dot(DJ[5], J[6 + j]));
-        }
-        Wll[0] += dot(DJ[6], J[6]); Wll[1] += dot(DJ[7], J[6]); Wll[2] += dot(DJ[7], J[7]);
-        Wll[3] += dot(DJ[8], J[6]); Wll[4] += dot(DJ[8], J[7]); Wll[5] += dot(DJ[8], J[8]);
-      }
-    }
+    const int4 cnt = L.cnt;
+    SV vbase; vbase.a = wb; vbase.l = vb;
+    contact_body<2>(L, P, cnt.x + cnt.y, cnt.z, L.j[2].m1.w, base_z, K.R[2], K.p[2], v[2], e_cl, S, K.p, f, W);
+    contact_body<1>(L, P, cnt.x, cnt.y, L.j[1].m1.w, base_z, K.R[1], K.p[1], v[1], e_cl, S, K.p, f, W);
+    contact_body<0>(L, P, 0, cnt.x, L.j[0].m1.w, base_z, K.R[0], K.p[0], v[0], e_cl, S, K.p, f, W);
+    contact_body<-1>(L, P, cnt.x + cnt.y + cnt.z, cnt.w, __int_as_float(L.meta.y), base_z, Rb, v3(0.f, 0.f, 0.f), vbase, e_cl,
+                     S, K.p, f, W);
   }
   // ---- composite inertias / forces, CRBA, RNEA bias ---------------------------------------------
   const RBI Ic2 = I[2], Ic1 = I[1] + Ic2, Ic0 = I[0] + Ic1;
@@ -237,7 +281,7 @@ ORL_DI void leg_dynamics(const orl_leg_model& L, const orl_robot_model& Mo, cons
   A[0] = sdot(S[0], Fk[0]);
   A[1] = sdot(S[0], Fk[1]); A[2] = sdot(S[1], Fk[1]);
   A[3] = sdot(S[0], Fk[2]); A[4] = sdot(S[1], Fk[2]); A[5] = sdot(S[2], Fk[2]);
-  float C0 = sdot(S[0], fc0), C1 = sdot(S[1], fc1), C2 = sdot(S[2], fc2);
+  const float C0 = sdot(S[0], fc0), C1 = sdot(S[1], fc1), C2 = sdot(S[2], fc2);
   if (EXPORT) {
 #pragma unroll
     for (int i = 0; i < 6; ++i) ex->Hll[i] = A[i];
@@ -246,11 +290,15 @@ ORL_DI void leg_dynamics(const orl_leg_model& L, const orl_robot_model& Mo, cons
     ex->C[0] = C0; ex->C[1] = C1; ex->C[2] = C2;
   }
   // ---- lane-local Schur complement ---------------------------------------------------------------
-#pragma unroll
-  for (int i = 0; i < 6; ++i) A[i] += Wll[i];
   SV B[3];
 #pragma unroll
-  for (int k = 0; k < 3; ++k) B[k] = Fk[k] + Wbl[k];
+  for (int k = 0; k < 3; ++k) B[k] = Fk[k];
+  if (CONTACT && W.any) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) A[i] += W.Wll[i];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) B[k] = B[k] + W.Wbl[k];
+  }
   const LDL3 fac = ldl3(A);
   float r0 = tau[0] - C0, r1 = tau[1] - C1, r2 = tau[2] - C2;
   ldl3_solve(fac, r0, r1, r2);                 // y_r = A^-1 r
@@ -273,12 +321,16 @@ ORL_DI void leg_dynamics(const orl_leg_model& L, const orl_robot_model& Mo, cons
   for (int a = 0; a < 6; ++a)
 #pragma unroll
     for (int b = 0; b <= a; ++b)
-      red[TRI(a, b)] += Wbb[TRI(a, b)] - (Bm[a][0] * Y[0][b] + Bm[a][1] * Y[1][b] + Bm[a][2] * Y[2][b]);
-  {
-    const float pbv[6] = {fc0.a.x - fb_ext.a.x, fc0.a.y - fb_ext.a.y, fc0.a.z - fb_ext.a.z,
-                          fc0.l.x - fb_ext.l.x, fc0.l.y - fb_ext.l.y, fc0.l.z - fb_ext.l.z};
+      red[TRI(a, b)] = fmaf(-Bm[a][0], Y[0][b], fmaf(-Bm[a][1], Y[1][b], fmaf(-Bm[a][2], Y[2][b], red[TRI(a, b)])));
+  if (CONTACT && W.any) {
 #pragma unroll
-    for (int a = 0; a < 6; ++a) red[21 + a] = -pbv[a] - (Bm[a][0] * r0 + Bm[a][1] * r1 + Bm[a][2] * r2);
+    for (int i = 0; i < 21; ++i) red[i] += W.Wbb[i];
+  }
+  {
+    const float pbv[6] = {fc0.a.x - W.fb_ext.a.x, fc0.a.y - W.fb_ext.a.y, fc0.a.z - W.fb_ext.a.z,
+                          fc0.l.x - W.fb_ext.l.x, fc0.l.y - W.fb_ext.l.y, fc0.l.z - W.fb_ext.l.z};
+#pragma unroll
+    for (int a = 0; a < 6; ++a) red[21 + a] = fmaf(-Bm[a][0], r0, fmaf(-Bm[a][1], r1, fmaf(-Bm[a][2], r2, -pbv[a])));
   }
   if (EXPORT) {
     // un-modified base block and base bias need their own reduction (no W, no Schur term)
@@ -296,22 +348,24 @@ ORL_DI void leg_dynamics(const orl_leg_model& L, const orl_robot_model& Mo, cons
   for (int i = 0; i < 27; ++i) red[i] = quad_sum(red[i]);
   // ---- base body itself (computed redundantly by the 4 lanes) --------------------------------------
   {
-    S3 Ib = {Mo.base_inertia[0], Mo.base_inertia[1], Mo.base_inertia[2], Mo.base_inertia[3], Mo.base_inertia[4], Mo.base_inertia[5]};
-    RBI Bb = body_inertia(Mo.base_mass, v3(0.f, 0.f, 0.f), rot_sym(Rb, Ib));
-    SV vb6; vb6.a = wb; vb6.l = vb;
-    SV a0; a0.a = v3(0.f, 0.f, 0.f); a0.l = v3(0.f, 0.f, P.g);
-    SV fbody = apply(Bb, a0) + crf(vb6, apply(Bb, vb6));
-    float tb[21];
-    rbi_to_tri(Bb, tb);
-#pragma unroll
-    for (int i = 0; i < 21; ++i) red[i] += tb[i];
-    red[21] -= fbody.a.x; red[22] -= fbody.a.y; red[23] -= fbody.a.z;
-    red[24] -= fbody.l.x; red[25] -= fbody.l.y; red[26] -= fbody.l.z;
+    const float4 b0 = Mo.b0, b1 = Mo.b1;
+    const S3 Ib = {b0.y, b0.z, b0.w, b1.x, b1.y, b1.z};
+    const S3 IbA = rot_sym(Rb, Ib);
+    // COM at the origin: I = diag(IbA, m); bias force = I a0 + v x* I v = [w x (IbA w) ; m (g e_z + w x v)]
+    const float3 Iw = mul(IbA, wb);
+    const float3 fa = cross(wb, Iw);
+    const float3 fl = b0.x * cross_add(wb, vb, v3(0.f, 0.f, P.g));
+    red[TRI(0, 0)] += IbA.xx; red[TRI(1, 0)] += IbA.xy; red[TRI(1, 1)] += IbA.yy;
+    red[TRI(2, 0)] += IbA.xz; red[TRI(2, 1)] += IbA.yz; red[TRI(2, 2)] += IbA.zz;
+    red[TRI(3, 3)] += b0.x; red[TRI(4, 4)] += b0.x; red[TRI(5, 5)] += b0.x;
+    red[21] -= fa.x; red[22] -= fa.y; red[23] -= fa.z;
+    red[24] -= fl.x; red[25] -= fl.y; red[26] -= fl.z;
     if (EXPORT) {
-#pragma unroll
-      for (int i = 0; i < 21; ++i) ex->Hbb[i] += tb[i];
-      ex->pb[0] += fbody.a.x; ex->pb[1] += fbody.a.y; ex->pb[2] += fbody.a.z;
-      ex->pb[3] += fbody.l.x; ex->pb[4] += fbody.l.y; ex->pb[5] += fbody.l.z;
+      ex->Hbb[TRI(0, 0)] += IbA.xx; ex->Hbb[TRI(1, 0)] += IbA.xy; ex->Hbb[TRI(1, 1)] += IbA.yy;
+      ex->Hbb[TRI(2, 0)] += IbA.xz; ex->Hbb[TRI(2, 1)] += IbA.yz; ex->Hbb[TRI(2, 2)] += IbA.zz;
+      ex->Hbb[TRI(3, 3)] += b0.x; ex->Hbb[TRI(4, 4)] += b0.x; ex->Hbb[TRI(5, 5)] += b0.x;
+      ex->pb[0] += fa.x; ex->pb[1] += fa.y; ex->pb[2] += fa.z;
+      ex->pb[3] += fl.x; ex->pb[4] += fl.y; ex->pb[5] += fl.z;
     }
   }
   float ab[6] = {red[21], red[22], red[23], red[24], red[25], red[26]};
@@ -320,5 +374,7 @@ ORL_DI void leg_dynamics(const orl_leg_model& L, const orl_robot_model& Mo, cons
   alin_b = v3(ab[3], ab[4], ab[5]);
   qdd[0] = r0; qdd[1] = r1; qdd[2] = r2;
 #pragma unroll
-  for (int c = 0; c < 6; ++c) { qdd[0] -= Y[0][c] * ab[c]; qdd[1] -= Y[1][c] * ab[c]; qdd[2] -= Y[2][c] * ab[c]; }
+  for (int c = 0; c < 6; ++c) {
+    qdd[0] = fmaf(-Y[0][c], ab[c], qdd[0]); qdd[1] = fmaf(-Y[1][c], ab[c], qdd[1]); qdd[2] = fmaf(-Y[2][c], ab[c], qdd[2]);
+  }
 }

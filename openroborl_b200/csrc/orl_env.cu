@@ -23,7 +23,7 @@ struct orl_env {
   std::string err;
   // device allocations
   float* d_state;
-  orl_robot_model* d_model;
+  DevModel* d_model;
   double* d_stats;
   std::vector<void*> d_motion;     // owned motion-table buffers
   // host copies of the motion tables (tests / diagnostics)
@@ -99,8 +99,59 @@ static void fill_dev_cfg(orl_env* e) {
   d.fb0 = (float)(K * K * norm); d.fb1 = (float)(2.0 * K * K * norm); d.fb2 = d.fb0;
   d.fa1 = (float)(2.0 * (K * K - 1.0) * norm); d.fa2 = (float)((1.0 - M_SQRT2 * K + K * K) * norm);
   d.phys.dt = (float)c.sim_time_step; d.phys.g = -c.gravity_z;
-  d.phys.kn = c.contact_kn; d.phys.bn = c.contact_bn; d.phys.d0 = c.contact_d0; d.phys.bt = c.contact_bt;
-  d.phys.klim = c.limit_k; d.phys.dlim = c.limit_d; d.phys.e0 = c.limit_e0;
+  d.phys.kn = c.contact_kn; d.phys.bn = c.contact_bn; d.phys.inv_d0 = 1.0f / c.contact_d0; d.phys.bt = c.contact_bt;
+  d.phys.klim = c.limit_k; d.phys.dlim = c.limit_d; d.phys.inv_e0 = 1.0f / c.limit_e0;
+}
+
+static float f_from_i(int32_t i) { float f; memcpy(&f, &i, 4); return f; }
+static int32_t i_from_f(float f) { int32_t i; memcpy(&i, &f, 4); return i; }
+
+// orl_robot_model (public, plain arrays) -> DevModel (float4 packed; collision points grouped per body)
+static void pack_model(const orl_robot_model& m, DevModel& d) {
+  memset(&d, 0, sizeof(d));
+  d.b0 = make_float4(m.base_mass, m.base_inertia[0], m.base_inertia[1], m.base_inertia[2]);
+  d.b1 = make_float4(m.base_inertia[3], m.base_inertia[4], m.base_inertia[5], m.max_angle_change);
+  d.ipos = make_float4(m.init_pos[0], m.init_pos[1], m.init_pos[2], 0.f);
+  d.iquat = make_float4(m.init_quat[0], m.init_quat[1], m.init_quat[2], m.init_quat[3]);
+  for (int l = 0; l < ORL_NUM_LEGS; ++l) {
+    const orl_leg_model& L = m.leg[l];
+    DevLeg& D = d.leg[l];
+    float brad[4] = {0.f, 0.f, 0.f, 0.f}, mmax = 0.f;     // bodies 0,1,2 and base
+    int cnt[4] = {0, 0, 0, 0}, pos = 0;
+    for (int g = 0; g < 4; ++g) {
+      const int body = g == 3 ? -1 : g;
+      for (int i = 0; i < L.n_cp; ++i) {
+        const orl_contact_point& c = L.cp[i];
+        if (c.body != body) continue;
+        D.cp[pos].a = make_float4(c.local[0], c.local[1], c.local[2], c.radius);
+        D.cp[pos].b = make_float4(c.mu, c.margin, f_from_i(c.is_foot ? 1 : 0), 0.f);
+        const float r = sqrtf(c.local[0] * c.local[0] + c.local[1] * c.local[1] + c.local[2] * c.local[2]) + c.radius;
+        if (r > brad[g]) brad[g] = r;
+        if (!c.is_foot && c.margin > mmax) mmax = c.margin;
+        ++pos; ++cnt[g];
+      }
+    }
+    for (int k = 0; k < 3; ++k) {
+      DevJoint& J = D.j[k];
+      J.r0 = make_float4(L.R_fix[k][0], L.R_fix[k][1], L.R_fix[k][2], L.p_fix[k][0]);
+      J.r1 = make_float4(L.R_fix[k][3], L.R_fix[k][4], L.R_fix[k][5], L.p_fix[k][1]);
+      J.r2 = make_float4(L.R_fix[k][6], L.R_fix[k][7], L.R_fix[k][8], L.p_fix[k][2]);
+      J.i0 = make_float4(L.inertia[k][0], L.inertia[k][1], L.inertia[k][2], L.inertia[k][3]);
+      J.i1 = make_float4(L.inertia[k][4], L.inertia[k][5], L.mass[k], L.com[k][0]);
+      J.c1 = make_float4(L.com[k][1], L.com[k][2], L.lower[k], L.upper[k]);
+      J.m0 = make_float4(L.damping[k], L.dir[k], L.offset[k], L.kp[k]);
+      J.m1 = make_float4(L.kd[k], L.init_angle[k], f_from_i(L.motor[k]), brad[k]);
+    }
+    for (int e = 0; e < 2; ++e)
+      D.ee[e] = make_float4(L.ee_local[e][0], L.ee_local[e][1], L.ee_local[e][2], f_from_i(L.ee_body[e]));
+    D.meta = make_int4(L.n_ee, i_from_f(brad[3]), i_from_f(mmax), 0);
+    D.cnt = make_int4(cnt[0], cnt[1], cnt[2], cnt[3]);
+  }
+  d.n_links = m.n_links;
+  for (int i = 0; i < ORL_MAX_LINKS; ++i) {
+    d.link_leg[i] = m.link_leg[i]; d.link_body[i] = m.link_body[i];
+    d.link_com[i] = make_float4(m.link_com[i][0], m.link_com[i][1], m.link_com[i][2], 0.f);
+  }
 }
 
 extern "C" int orl_create(const orl_config* cfg, const orl_robot_model* model, orl_env** out) {
@@ -124,7 +175,12 @@ extern "C" int orl_create(const orl_config* cfg, const orl_robot_model* model, o
     if (model->leg[l].n_ee < 0 || model->leg[l].n_ee > 2) return fail(e, ORL_ERR_INVALID, "bad n_ee on leg %d", l);
     for (int k = 0; k < 3; ++k)
       if (model->leg[l].motor[k] < 0 || model->leg[l].motor[k] >= 12) return fail(e, ORL_ERR_INVALID, "bad motor index");
+    for (int i = 0; i < model->leg[l].n_cp; ++i)
+      if (model->leg[l].cp[i].body < -1 || model->leg[l].cp[i].body > 2) return fail(e, ORL_ERR_INVALID, "bad collision-point body");
+    for (int i = 0; i < model->leg[l].n_ee; ++i)
+      if (model->leg[l].ee_body[i] < 0 || model->leg[l].ee_body[i] > 2) return fail(e, ORL_ERR_INVALID, "bad end-effector body");
   }
+  if (!(cfg->contact_d0 > 0) || !(cfg->limit_e0 > 0)) return fail(e, ORL_ERR_INVALID, "contact_d0 and limit_e0 must be positive");
   e->device = cfg->device;
   CUDA_TRY(e, cudaSetDevice(e->device));
   const size_t nstate = (size_t)cfg->num_robot * ORL_STRIDE;
@@ -132,7 +188,11 @@ extern "C" int orl_create(const orl_config* cfg, const orl_robot_model* model, o
   CUDA_TRY(e, cudaMemset(e->d_state, 0, nstate * sizeof(float)));
   CUDA_TRY(e, cudaMalloc(&e->d_model, ORL_SMEM_MODEL_BYTES));
   CUDA_TRY(e, cudaMemset(e->d_model, 0, ORL_SMEM_MODEL_BYTES));
-  CUDA_TRY(e, cudaMemcpy(e->d_model, model, sizeof(orl_robot_model), cudaMemcpyHostToDevice));
+  {
+    DevModel packed;
+    pack_model(*model, packed);
+    CUDA_TRY(e, cudaMemcpy(e->d_model, &packed, sizeof(DevModel), cudaMemcpyHostToDevice));
+  }
   CUDA_TRY(e, cudaMalloc(&e->d_stats, 4 * sizeof(double)));
   CUDA_TRY(e, cudaMemset(e->d_stats, 0, 4 * sizeof(double)));
   // motor strengths default to 1, orientation of the control observation to identity

@@ -29,13 +29,13 @@ struct DevCfg {
 
 struct DevEnv {
   float* state;                       // [n][ORL_STRIDE]
-  const orl_robot_model* model;       // device copy
+  const DevModel* model;              // device copy (packed, float4 aligned)
   MotionTables mt;
   DevCfg cfg;
   double* stats;                      // [4]
 };
 
-#define ORL_SMEM_MODEL_BYTES ((sizeof(orl_robot_model) + 15) / 16 * 16)
+#define ORL_SMEM_MODEL_BYTES ((sizeof(DevModel) + 15) / 16 * 16)
 #define ORL_SMEM_BYTES (ORL_SMEM_MODEL_BYTES + ORL_ROBOTS_PER_WARP * (ORL_STRIDE + ORL_OBS_SIZE) * 4)
 
 ORL_DI int& as_int(float& f) { return *reinterpret_cast<int*>(&f); }
@@ -43,13 +43,12 @@ ORL_DI double ld_f64(const float* p) { return *reinterpret_cast<const double*>(p
 ORL_DI void st_f64(float* p, double v) { *reinterpret_cast<double*>(p) = v; }
 
 // ---- shared-memory staging ---------------------------------------------------------------------
-ORL_DI void stage_in(const DevEnv& E, unsigned char* smem, const orl_robot_model*& Mo, float*& st, float*& ob) {
+ORL_DI void stage_in(const DevEnv& E, unsigned char* smem, const DevModel*& Mo, float*& st, float*& ob) {
   const int lane = threadIdx.x;
   float4* m4 = reinterpret_cast<float4*>(smem);
   const float4* g4 = reinterpret_cast<const float4*>(E.model);
-  for (int i = lane; i < (int)(ORL_SMEM_MODEL_BYTES / 16); i += 32)
-    if ((size_t)i * 16 < sizeof(orl_robot_model)) m4[i] = g4[i];
-  Mo = reinterpret_cast<const orl_robot_model*>(smem);
+  for (int i = lane; i < (int)(ORL_SMEM_MODEL_BYTES / 16); i += 32) m4[i] = g4[i];
+  Mo = reinterpret_cast<const DevModel*>(smem);
   st = reinterpret_cast<float*>(smem + ORL_SMEM_MODEL_BYTES);
   ob = st + ORL_ROBOTS_PER_WARP * ORL_STRIDE;
   const int row0 = blockIdx.x * ORL_ROBOTS_PER_WARP;
@@ -107,8 +106,7 @@ ORL_DI double motion_time(float* S, const DevCfg& C) {
   if (as_int(S[S_WARM])) t = __dsub_rn(t, C.warmup_time);
   return t;
 }
-ORL_DI M3 pickR(const LegFK& K, int kb) { return kb == 0 ? K.R[0] : (kb == 1 ? K.R[1] : K.R[2]); }
-ORL_DI float3 pickp(const LegFK& K, int kb) { return kb == 0 ? K.p[0] : (kb == 1 ? K.p[1] : K.p[2]); }
+ORL_DI Q4 ldq4(float4 v) { return q4(v.x, v.y, v.z, v.w); }
 
 // Observation rows: sensor histories (already in the record) + the target frames.
 // ImitationTask.build_target_obs (imitation_task.py:254-301): lane j of the quad builds frame j.
@@ -142,9 +140,9 @@ ORL_DI void build_obs(float* S, float* O, const DevEnv& E, int leg) {
 // Episode reset of one robot, executed by its quad on the staged record.
 // Minitaur.reset (minitaur.py:232-278) + ImitationTask.reset/_reset_ref_motion/_sync_sim_model
 // (imitation_task.py:166-199, 694-732, 778-793).  `qmask` = the 4 lanes of this quad.
-ORL_DI void reset_robot(float* S, const DevEnv& E, const orl_robot_model& Mo, int gid, int leg, unsigned qmask) {
+ORL_DI void reset_robot(float* S, const DevEnv& E, const DevModel& Mo, int gid, int leg, unsigned qmask) {
   const DevCfg& C = E.cfg;
-  const orl_leg_model& L = Mo.leg[leg];
+  const DevLeg& L = Mo.leg[leg];
   const int episode = as_int(S[S_EPISODE]);
   uint32_t ra[4], rb[4];
   philox4x32((uint32_t)gid, (uint32_t)episode, 0u, 0u, (uint32_t)(C.seed & 0xffffffffull), (uint32_t)(C.seed >> 32), ra);
@@ -160,8 +158,8 @@ ORL_DI void reset_robot(float* S, const DevEnv& E, const orl_robot_model& Mo, in
   // per-motor fields owned by this lane
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
-    const int m = L.motor[k];
-    const float qm_def = L.init_angle[k] * L.dir[k];                // true motor angle of the default pose
+    const int m = __float_as_int(L.j[k].m1.z);
+    const float qm_def = L.j[k].m1.y * L.j[k].m0.y;                 // true motor angle of the default pose (INIT * DIR)
     S[S_FX + m] = 0.f; S[S_FX + 12 + m] = 0.f; S[S_FY + m] = 0.f; S[S_FY + 12 + m] = 0.f;   // action_filter.py:103-109
     S[S_PREV + m] = 0.f;
     S[S_RING1 + m] = qm_def; S[S_RING2 + m] = qm_def;
@@ -187,8 +185,8 @@ ORL_DI void reset_robot(float* S, const DevEnv& E, const orl_robot_model& Mo, in
   const RefSample s = ref_sample(E.mt, F, time);
   float3 p0; Q4 r0;
   ref_root(E.mt, F, s, true, p0, r0);
-  const float3 sim_pos = ld3(Mo.init_pos);
-  const Q4 sim_rot = ldq(Mo.init_quat);
+  const float3 sim_pos = f4xyz(Mo.ipos);
+  const Q4 sim_rot = ldq4(Mo.iquat);
   float3 op = sim_pos - p0; op.z = 0.f;
   const float dh = qheading(sim_rot) - qheading(r0);
   F.origin_pos = op;
@@ -220,7 +218,7 @@ ORL_DI void reset_robot(float* S, const DevEnv& E, const orl_robot_model& Mo, in
 __global__ void __launch_bounds__(32) orl_step_kernel(DevEnv E, const float* __restrict__ actions, float* __restrict__ obs_out,
                                                       float* __restrict__ reward_out, uint8_t* __restrict__ done_out) {
   extern __shared__ __align__(16) unsigned char smem[];
-  const orl_robot_model* Mo; float* st; float* ob;
+  const DevModel* Mo; float* st; float* ob;
   stage_in(E, smem, Mo, st, ob);
   const DevCfg& C = E.cfg;
   const int lane = threadIdx.x, leg = lane & 3, rw = lane >> 2;
@@ -229,7 +227,7 @@ __global__ void __launch_bounds__(32) orl_step_kernel(DevEnv E, const float* __r
   const int robot_c = min(robot, C.n - 1);
   float* S = st + rw * ORL_STRIDE;
   float* O = ob + rw * ORL_OBS_SIZE;
-  const orl_leg_model& L = Mo->leg[leg];
+  const DevLeg& L = Mo->leg[leg];
   const PhysParams P = C.phys;
 
   // ---- registers -----------------------------------------------------------------------------
@@ -237,19 +235,22 @@ __global__ void __launch_bounds__(32) orl_step_kernel(DevEnv E, const float* __r
   Q4 quat = ldq(S + S_QUAT);
   float q[3], qd[3], target[3], act[3], prevf[3], r1[3], r2[3], strength[3];
   int mi[3];
+  float j_dir[3], j_off[3], j_kp[3], j_kd[3], j_lo[3], j_up[3], j_damp[3];
   const int substep0 = as_int(S[S_SUBSTEP]);
   const bool first_step = as_int(S[S_STEP]) == 0;
   // 1. set_act: a += INIT; Butterworth (minitaur.py:280-285, 1169-1178; action_filter.py:111-127)
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
-    const int m = L.motor[k];
+    const float4 c1 = L.j[k].c1, m0 = L.j[k].m0, m1 = L.j[k].m1;
+    const int m = __float_as_int(m1.z);
     mi[k] = m;
+    j_lo[k] = c1.z; j_up[k] = c1.w; j_damp[k] = m0.x; j_dir[k] = m0.y; j_off[k] = m0.z; j_kp[k] = m0.w; j_kd[k] = m1.x;
     q[k] = S[S_Q + 3 * leg + k]; qd[k] = S[S_QD + 3 * leg + k];
     r1[k] = S[S_RING1 + m]; r2[k] = S[S_RING2 + m];
     prevf[k] = S[S_PREV + m]; strength[k] = S[S_STRENGTH + m];
-    act[k] = __ldg(actions + (size_t)robot_c * 12 + m) + L.init_angle[k];
+    act[k] = __ldg(actions + (size_t)robot_c * 12 + m) + m1.y;
     float x0 = S[S_FX + m], x1 = S[S_FX + 12 + m], y0 = S[S_FY + m], y1 = S[S_FY + 12 + m];
-    if (substep0 == 0) { const float d = wrap_pi(r2[k]); x0 = x1 = y0 = y1 = d; }
+    if (substep0 == 0) { const float d = wrap_pi_fast(r2[k]); x0 = x1 = y0 = y1 = d; }
     const float y = act[k] * C.fb0 + (x0 * C.fb1 + x1 * C.fb2) - (y0 * C.fa1 + y1 * C.fa2);
     S[S_FX + m] = act[k]; S[S_FX + 12 + m] = x0; S[S_FY + m] = y; S[S_FY + 12 + m] = y0;
     target[k] = y;
@@ -257,7 +258,8 @@ __global__ void __launch_bounds__(32) orl_step_kernel(DevEnv E, const float* __r
   // 2. physics substeps (quadruped_gym_env.py:220-225)
   Q4 obs_q = ldq(S + S_OBSQ);
   float3 obs_w = v3(0.f, 0.f, 0.f);
-  const Q4 init_inv = qconj(ldq(Mo->init_quat));
+  const Q4 init_inv = qconj(ldq4(Mo->iquat));
+  const float mac = Mo->b1.w;
   const int AR = C.action_repeat;
   const float inv_ar = 1.0f / (float)AR;
   for (int s = 0; s < AR; ++s) {
@@ -266,36 +268,43 @@ __global__ void __launch_bounds__(32) orl_step_kernel(DevEnv E, const float* __r
     float tau[3], qm_now[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      const float qobs = wrap_pi(r2[k]);                               // get_motor_angles(): delayed + wrapped
+      const float qobs = wrap_pi_fast(r2[k]);                          // get_motor_angles(): delayed + wrapped
       const float prev = first_step ? qobs : prevf[k];                 // minitaur.py:450-453
-      float cmd = prev + lerp * (target[k] - prev);                    // :455-456
-      cmd = fminf(fmaxf(cmd, qobs - Mo->max_angle_change), qobs + Mo->max_angle_change);   // :706-723
-      const float qm = (q[k] - L.offset[k]) * L.dir[k];                // :549-553
-      const float qdm = qd[k] * L.dir[k];                              // :575-578
-      const float tm = strength[k] * (-1.0f * (L.kp[k] * (qm - cmd)) - L.kd[k] * qdm);     // minitaur_motor.py:163-166
-      const float e = fmaxf(0.f, L.lower[k] - q[k]) - fmaxf(0.f, q[k] - L.upper[k]);
-      tau[k] = tm * L.dir[k] + P.klim * e - P.dlim * fminf(1.0f, fabsf(e) / P.e0) * qd[k] - L.damping[k] * qd[k];
+      float cmd = fmaf(lerp, target[k] - prev, prev);                  // :455-456
+      cmd = fminf(fmaxf(cmd, qobs - mac), qobs + mac);                 // :706-723
+      const float qm = (q[k] - j_off[k]) * j_dir[k];                   // :549-553
+      const float qdm = qd[k] * j_dir[k];                              // :575-578
+      const float tm = strength[k] * (-1.0f * (j_kp[k] * (qm - cmd)) - j_kd[k] * qdm);     // minitaur_motor.py:163-166
+      const float e = fmaxf(0.f, j_lo[k] - q[k]) - fmaxf(0.f, q[k] - j_up[k]);
+      tau[k] = fmaf(tm, j_dir[k], fmaf(P.klim, e, -(fmaf(P.dlim, fminf(1.0f, fabsf(e) * P.inv_e0), j_damp[k])) * qd[k]));
       qm_now[k] = qm;
     }
     float3 alpha, alin; float qdd[3];
-    leg_dynamics<true, false>(L, *Mo, P, Rb, pos.z, ang, lin, q, qd, tau, alpha, alin, qdd, nullptr);
+    leg_dynamics<true, false, true>(L, *Mo, P, Rb, pos.z, ang, lin, q, qd, tau, alpha, alin, qdd, nullptr);
     // semi-implicit Euler: velocities first, then positions with the new velocities
-    const float3 lin_dot = alin + cross(ang, lin);
-    ang = ang + P.dt * alpha;
-    lin = lin + P.dt * lin_dot;
-    pos = pos + P.dt * lin;
+    const float3 lin_dot = cross_add(ang, lin, alin);
+    ang = fma3(P.dt, alpha, ang);
+    lin = fma3(P.dt, lin_dot, lin);
+    pos = fma3(P.dt, lin, pos);
     {
-      const float wn = sqrtf(dot(ang, ang));
-      const float half = 0.5f * wn * P.dt;
-      float sh, ch;
-      sincosf(half, &sh, &ch);
-      const float kk = wn > 1e-12f ? sh / wn : 0.5f * P.dt;
+      // quaternion exponential of w*dt: sin(h)/|w| and cos(h), h = |w| dt / 2, by Taylor series while h < 0.05
+      const float h2 = 0.25f * P.dt * P.dt * dot(ang, ang);
+      float kk, ch;
+      if (h2 < 2.5e-3f) {
+        kk = 0.5f * P.dt * fmaf(h2, fmaf(h2, 1.0f / 120.0f, -1.0f / 6.0f), 1.0f);
+        ch = fmaf(h2, fmaf(h2, 1.0f / 24.0f, -0.5f), 1.0f);
+      } else {
+        const float wn = sqrtf(dot(ang, ang));
+        float sh;
+        sincosf(0.5f * wn * P.dt, &sh, &ch);
+        kk = sh / wn;
+      }
       quat = qnormalize(qmul(q4(ang.x * kk, ang.y * kk, ang.z * kk, ch), quat));
     }
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      qd[k] += P.dt * qdd[k];
-      q[k] += P.dt * qd[k];
+      qd[k] = fmaf(P.dt, qdd[k], qd[k]);
+      q[k] = fmaf(P.dt, qd[k], q[k]);
       r2[k] = r1[k]; r1[k] = qm_now[k];
     }
     if (s == AR - 3) {   // the control observation at the end of the step is 2 substeps old (minitaur.py:336-357)
@@ -312,7 +321,7 @@ __global__ void __launch_bounds__(32) orl_step_kernel(DevEnv E, const float* __r
     // 3. sensors.on_step (sensor_wrappers.py:131-135): newest first
     S[S_ACT + 24 + mi[k]] = S[S_ACT + 12 + mi[k]]; S[S_ACT + 12 + mi[k]] = S[S_ACT + mi[k]]; S[S_ACT + mi[k]] = act[k];
     S[S_ANGH + 24 + mi[k]] = S[S_ANGH + 12 + mi[k]]; S[S_ANGH + 12 + mi[k]] = S[S_ANGH + mi[k]];
-    S[S_ANGH + mi[k]] = wrap_pi(r2[k]);
+    S[S_ANGH + mi[k]] = wrap_pi_fast(r2[k]);
   }
   const int substep1 = substep0 + AR;
   const int envstep1 = as_int(S[S_ENVSTEP]) + 1;
@@ -330,7 +339,7 @@ __global__ void __launch_bounds__(32) orl_step_kernel(DevEnv E, const float* __r
   // 4. reward against the reference state of the END of the previous step (imitation_task.py:341-516)
   const M3 Rb = qmat(quat);
   LegFK Ks, Kr;
-  leg_fk(L, Rb, q, Ks);
+  leg_fk<false>(L, Rb, q, Ks);
   const float3 rp = ld3(S + S_REFPOSE);
   const Q4 rq = ldq(S + S_REFPOSE + 3);
   float rj[3];
@@ -341,15 +350,16 @@ __global__ void __launch_bounds__(32) orl_step_kernel(DevEnv E, const float* __r
     const float dq = rj[k] - q[k], dv = S[S_REFVEL + 6 + 3 * leg + k] - qd[k];
     pose_err += dq * dq; vel_err += dv * dv;
   }
-  leg_fk(L, qmat(rq), rj, Kr);
+  leg_fk<false>(L, qmat(rq), rj, Kr);
   {
-    const Q4 inv_def = qconj(ldq(Mo->init_quat));                      // default root rotation, :1071-1075, 1245-1252
+    const Q4 inv_def = qconj(ldq4(Mo->iquat));                      // default root rotation, :1071-1075, 1245-1252
     float ss, cs, sr, cr;
     sincosf(-qheading(qmul(quat, inv_def)), &ss, &cs);
     sincosf(-qheading(qmul(rq, inv_def)), &sr, &cr);
-    for (int e = 0; e < L.n_ee; ++e) {
-      const int kb = L.ee_body[e];
-      const float3 loc = ld3(L.ee_local[e]);
+    for (int e = 0; e < L.meta.x; ++e) {
+      const float4 ee = L.ee[e];
+      const int kb = __float_as_int(ee.w);
+      const float3 loc = f4xyz(ee);
       const float3 es = pickp(Ks, kb) + mul(pickR(Ks, kb), loc);       // rel. sim root
       const float3 er = pickp(Kr, kb) + mul(pickR(Kr, kb), loc);       // rel. ref root
       const float3 d = qrot_z(sr, cr, er) - qrot_z(ss, cs, es);
@@ -396,13 +406,24 @@ __global__ void __launch_bounds__(32) orl_step_kernel(DevEnv E, const float* __r
   }
   // 6. termination against the freshly updated reference (imitation_task.py:518-572, wrapper_env.py:78-80)
   int fall = 0;
-  for (int i = 0; i < L.n_cp; ++i) {
-    const orl_contact_point& cp = L.cp[i];
-    if (cp.is_foot) continue;
-    const int kb = cp.body;
-    const float3 loc = ld3(cp.local);
-    const float z = pos.z + (kb < 0 ? dot(Rb.r2, loc) : pickp(Ks, kb).z + dot(pickR(Ks, kb).r2, loc)) - cp.radius - cp.margin;
-    fall |= (z < 0.f);
+  {
+    const int4 cnt = L.cnt;
+    const float mmax = __int_as_float(L.meta.z);          // largest margin of a non-foot point
+    const int first[4] = {0, cnt.x, cnt.x + cnt.y, cnt.x + cnt.y + cnt.z};
+    const int num[4] = {cnt.x, cnt.y, cnt.z, cnt.w};
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const M3 Rk = b == 3 ? Rb : Ks.R[b == 3 ? 0 : b];
+      const float oz = pos.z + (b == 3 ? 0.f : Ks.p[b == 3 ? 0 : b].z);
+      const float brad = b == 3 ? __int_as_float(L.meta.y) : L.j[b == 3 ? 0 : b].m1.w;
+      if (oz < brad + mmax) {
+        for (int i = first[b]; i < first[b] + num[b]; ++i) {
+          const float4 a = L.cp[i].a, bb = L.cp[i].b;
+          const float z = oz + dot(Rk.r2, f4xyz(a)) - a.w - bb.y;
+          fall |= (__float_as_int(bb.z) == 0) && (z < 0.f);
+        }
+      }
+    }
   }
   fall = quad_or(fall);      // Minitaur.step_counter > 0 always holds after a step (imitation_task.py:539)
   int done;
@@ -443,7 +464,7 @@ __global__ void __launch_bounds__(32) orl_step_kernel(DevEnv E, const float* __r
 // =================================================================================================
 __global__ void __launch_bounds__(32) orl_reset_kernel(DevEnv E, const uint8_t* __restrict__ mask, float* __restrict__ obs_out) {
   extern __shared__ __align__(16) unsigned char smem[];
-  const orl_robot_model* Mo; float* st; float* ob;
+  const DevModel* Mo; float* st; float* ob;
   stage_in(E, smem, Mo, st, ob);
   const int lane = threadIdx.x, leg = lane & 3, rw = lane >> 2;
   const int robot = blockIdx.x * ORL_ROBOTS_PER_WARP + rw;
@@ -484,33 +505,33 @@ __global__ void orl_motion_lookup_kernel(MotionTables T, const int32_t* clip, co
 }
 
 // one quad per query, model read from global memory (diagnostic paths, not performance critical)
-__global__ void orl_fk_kernel(const orl_robot_model* Mo, const float* pose, int n, float* com) {
+__global__ void orl_fk_kernel(const DevModel* Mo, const float* pose, int n, float* com) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int i = min(t >> 2, n - 1), leg = t & 3;
   const bool valid = (t >> 2) < n;
   const float* p = pose + (size_t)i * 19;
-  const orl_leg_model& L = Mo->leg[leg];
+  const DevLeg& L = Mo->leg[leg];
   float q[3] = {p[7 + 3 * leg], p[8 + 3 * leg], p[9 + 3 * leg]};
   LegFK K;
-  leg_fk(L, qmat(ldq(p + 3)), q, K);
+  leg_fk<false>(L, qmat(ldq(p + 3)), q, K);
   if (!valid) return;
   for (int l = 0; l < Mo->n_links; ++l) {
     if (Mo->link_leg[l] != leg) continue;
     const int kb = Mo->link_body[l];
-    const float3 c = ld3(p) + pickp(K, kb) + mul(pickR(K, kb), ld3(Mo->link_com[l]));
+    const float3 c = ld3(p) + pickp(K, kb) + mul(pickR(K, kb), f4xyz(Mo->link_com[l]));
     st3(com + ((size_t)i * Mo->n_links + l) * 3, c);
   }
 }
 
 // mode 0: mass matrix [n][18][18]; 1: inverse dynamics tau [n][18]; 2: forward dynamics acc [n][18]
 // generalised velocity order of the interface: [lin(3), ang(3), joints(12)]
-__global__ void orl_dyn_kernel(const orl_robot_model* Mo, PhysParams P, int mode, const float* pose, const float* vel,
+__global__ void orl_dyn_kernel(const DevModel* Mo, PhysParams P, int mode, const float* pose, const float* vel,
                                const float* in, int n, float* out) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int i = min(t >> 2, n - 1), leg = t & 3;
   const bool valid = (t >> 2) < n;
   const float* p = pose + (size_t)i * 19;
-  const orl_leg_model& L = Mo->leg[leg];
+  const DevLeg& L = Mo->leg[leg];
   float q[3] = {p[7 + 3 * leg], p[8 + 3 * leg], p[9 + 3 * leg]};
   float3 lin = v3(0.f, 0.f, 0.f), ang = v3(0.f, 0.f, 0.f);
   float qd[3] = {0.f, 0.f, 0.f}, tau[3] = {0.f, 0.f, 0.f};
@@ -523,8 +544,8 @@ __global__ void orl_dyn_kernel(const orl_robot_model* Mo, PhysParams P, int mode
   const M3 Rb = qmat(ldq(p + 3));
   float3 alpha, alin; float qdd[3];
   DynExport ex;
-  if (mode == 2) leg_dynamics<true, false>(L, *Mo, P, Rb, p[2], ang, lin, q, qd, tau, alpha, alin, qdd, nullptr);
-  else leg_dynamics<false, true>(L, *Mo, P, Rb, p[2], ang, lin, q, qd, tau, alpha, alin, qdd, &ex);
+  if (mode == 2) leg_dynamics<true, false, false>(L, *Mo, P, Rb, p[2], ang, lin, q, qd, tau, alpha, alin, qdd, nullptr);
+  else leg_dynamics<false, true, false>(L, *Mo, P, Rb, p[2], ang, lin, q, qd, tau, alpha, alin, qdd, &ex);
   if (mode == 2) {
     if (!valid) return;
     float* o = out + (size_t)i * 18;
@@ -587,8 +608,8 @@ __global__ void orl_reward_terms_kernel(DevEnv E, float* terms) {
   const bool valid = (t >> 2) < E.cfg.n;
   const DevCfg& C = E.cfg;
   float* S = E.state + (size_t)i * ORL_STRIDE;
-  const orl_robot_model* Mo = E.model;
-  const orl_leg_model& L = Mo->leg[leg];
+  const DevModel* Mo = E.model;
+  const DevLeg& L = Mo->leg[leg];
   const float3 pos = ld3(S + S_POS), lin = ld3(S + S_LIN), ang = ld3(S + S_ANG);
   const Q4 quat = ldq(S + S_QUAT);
   const float3 rp = ld3(S + S_REFPOSE);
@@ -600,15 +621,16 @@ __global__ void orl_reward_terms_kernel(DevEnv E, float* terms) {
     pose_err += dq * dq; vel_err += dv * dv;
   }
   LegFK Ks, Kr;
-  leg_fk(L, qmat(quat), q, Ks);
-  leg_fk(L, qmat(rq), rj, Kr);
-  const Q4 inv_def = qconj(ldq(Mo->init_quat));
+  leg_fk<false>(L, qmat(quat), q, Ks);
+  leg_fk<false>(L, qmat(rq), rj, Kr);
+  const Q4 inv_def = qconj(ldq4(Mo->iquat));
   float ss, cs, sr, cr;
   sincosf(-qheading(qmul(quat, inv_def)), &ss, &cs);
   sincosf(-qheading(qmul(rq, inv_def)), &sr, &cr);
-  for (int e = 0; e < L.n_ee; ++e) {
-    const int kb = L.ee_body[e];
-    const float3 loc = ld3(L.ee_local[e]);
+  for (int e = 0; e < L.meta.x; ++e) {
+    const float4 ee = L.ee[e];
+    const int kb = __float_as_int(ee.w);
+    const float3 loc = f4xyz(ee);
     const float3 es = pickp(Ks, kb) + mul(pickR(Ks, kb), loc);
     const float3 er = pickp(Kr, kb) + mul(pickR(Kr, kb), loc);
     const float3 d = qrot_z(sr, cr, er) - qrot_z(ss, cs, es);

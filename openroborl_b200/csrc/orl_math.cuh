@@ -26,8 +26,18 @@ ORL_DI float3 cross(float3 a, float3 b) {
   return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
 }
 ORL_DI float3 fma3(float s, float3 a, float3 b) { return v3(fmaf(s, a.x, b.x), fmaf(s, a.y, b.y), fmaf(s, a.z, b.z)); }
+// c + a x b with every product fused
+ORL_DI float3 cross_add(float3 a, float3 b, float3 c) {
+  return v3(fmaf(a.y, b.z, fmaf(-a.z, b.y, c.x)), fmaf(a.z, b.x, fmaf(-a.x, b.z, c.y)), fmaf(a.x, b.y, fmaf(-a.y, b.x, c.z)));
+}
+ORL_DI float fast_rcp(float x) { return __fdividef(1.0f, x); }
 
 ORL_DI float3 mul(const M3& R, float3 v) { return v3(dot(R.r0, v), dot(R.r1, v), dot(R.r2, v)); }
+// a + R v
+ORL_DI float3 madd(const M3& R, float3 v, float3 a) {
+  return v3(fmaf(R.r0.x, v.x, fmaf(R.r0.y, v.y, fmaf(R.r0.z, v.z, a.x))), fmaf(R.r1.x, v.x, fmaf(R.r1.y, v.y, fmaf(R.r1.z, v.z, a.y))),
+            fmaf(R.r2.x, v.x, fmaf(R.r2.y, v.y, fmaf(R.r2.z, v.z, a.z))));
+}
 ORL_DI float3 col(const M3& R, int c) {
   return c == 0 ? v3(R.r0.x, R.r1.x, R.r2.x) : (c == 1 ? v3(R.r0.y, R.r1.y, R.r2.y) : v3(R.r0.z, R.r1.z, R.r2.z));
 }
@@ -105,6 +115,8 @@ ORL_DI float wrap_pi(float a) {
   if (m >= ORL_PI_F) m -= ORL_TWO_PI_F; else if (m < -ORL_PI_F) m += ORL_TWO_PI_F;
   return m;
 }
+// identical to wrap_pi, without the fmodf loop in the (usual) case |a| < pi
+ORL_DI float wrap_pi_fast(float a) { return fabsf(a) < ORL_PI_F ? a : wrap_pi(a); }
 // pybullet.getEulerFromQuaternion (roll, pitch only) and yaw
 ORL_DI void bullet_euler(Q4 q, float& roll, float& pitch, float& yaw) {
   float sqx = q.x * q.x, sqy = q.y * q.y, sqz = q.z * q.z, squ = q.w * q.w;
