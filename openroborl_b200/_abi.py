@@ -101,7 +101,8 @@ SYMBOLS = {
     "orl_fp32_peak": (C.c_int, [C.c_int32, C.c_int32, _P]),
 }
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libopenroborl_b200.so")
+# ORL_LIB lets experiments load an alternative build of the same library (kernel-variant A/B runs)
+LIB_PATH = os.environ.get("ORL_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libopenroborl_b200.so")
 _lib = None
 
 

@@ -214,13 +214,22 @@ ORL_DI void contact_body(const DevLeg& L, const PhysParams& P, int first, int co
   const float oz = base_z + pk.z;
   if (!__any_sync(0xffffffffu, oz < brad)) return;       // warp-uniform skip: nobody's body KB is near the ground
   if (oz >= brad) return;
-  for (int i = first; i < first + count; ++i) {
-    const float4 a = L.cp[i].a;
+  // phase 1: penetration test of every point (independent iterations: the LDS.128 loads pipeline)
+  unsigned active = 0u;
+#pragma unroll 4
+  for (int i = 0; i < count; ++i) {
+    const float4 a = L.cp[first + i].a;
     const float z = oz + dot(Rk.r2, f4xyz(a)) - a.w;
-    if (z < 0.f) {
-      float3 r = madd(Rk, f4xyz(a), pk); r.z -= a.w;
-      contact_point<KB>(P, -z, L.cp[i].b.x, r, vk, e_cl, S, p, f, W);
-    }
+    active |= (z < 0.f ? 1u : 0u) << i;
+  }
+  // phase 2: the (few) penetrating points
+  while (active) {
+    const int i = __ffs(active) - 1;
+    active &= active - 1u;
+    const float4 a = L.cp[first + i].a;
+    const float z = oz + dot(Rk.r2, f4xyz(a)) - a.w;
+    float3 r = madd(Rk, f4xyz(a), pk); r.z -= a.w;
+    contact_point<KB>(P, -z, L.cp[first + i].b.x, r, vk, e_cl, S, p, f, W);
   }
 }
 

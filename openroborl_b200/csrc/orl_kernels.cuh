@@ -215,7 +215,10 @@ ORL_DI void reset_robot(float* S, const DevEnv& E, const DevModel& Mo, int gid, 
 // =================================================================================================
 // The fused control step (WrapperEnv.step): SURVEY.md A.3 steps 1-7.
 // =================================================================================================
-__global__ void __launch_bounds__(32) orl_step_kernel(DevEnv E, const float* __restrict__ actions, float* __restrict__ obs_out,
+#ifndef ORL_STEP_MIN_BLOCKS
+#define ORL_STEP_MIN_BLOCKS 8
+#endif
+__global__ void __launch_bounds__(32, ORL_STEP_MIN_BLOCKS) orl_step_kernel(DevEnv E, const float* __restrict__ actions, float* __restrict__ obs_out,
                                                       float* __restrict__ reward_out, uint8_t* __restrict__ done_out) {
   extern __shared__ __align__(16) unsigned char smem[];
   const DevModel* Mo; float* st; float* ob;
