@@ -11,10 +11,18 @@ Pinning status
 * Task logic (motion-file post-processing, frame lookup/interpolation, quaternion
   helpers, Butterworth filter, PD motor model, reward terms, termination, target
   observation, reset/RSI bookkeeping, observation pipeline): PINNED against the
-  reference's own, unmodified Python modules imported in the build container
-  (scripts/make_golden.py; fixtures under tests/golden/).  The third-party
-  `pybullet_utils.transformations` (pybullet==2.7.3, requirements.txt:5) is absent
-  from the container, so its published algorithm is restated in `oracle/xform.py`.
+  reference's own, unmodified Python modules imported in the build container:
+  - scripts/make_golden.py -> tests/golden/ref_motion_kat.npz: known answers of
+    motion_data.py / pose3d.py / action_filter.py / minitaur_motor.py
+    (tests/test_oracle_golden.py; frame indices and blend bit-exact);
+  - scripts/make_trace.py -> tests/golden/ref_task_trace.npz: step-by-step traces of the
+    reference's Minitaur + ImitationTask + LocomotionGymEnv + WrapperEnv classes running on
+    a fake BulletClient (scripts/fake_bullet.py) that serves the PyBullet calls from
+    oracle/rbd.py (tests/test_oracle_trace.py: observations 1e-6, rewards 1e-7, done flags
+    and the motion clock exact);
+  - the observation-space bounds serialised inside the reference's policy zips.
+  The third-party `pybullet_utils.transformations` (pybullet==2.7.3, requirements.txt:5) is
+  absent from the container, so its published algorithm is restated in `oracle/xform.py`.
 * Rigid-body arithmetic that the reference delegates to PyBullet 2.7.3
   (`stepSimulation`, `getLinkState`, contacts): PARITY UNPINNED.  PyBullet is not
   installable here (no wheel, no network), so forward kinematics, the mass matrix,

@@ -196,7 +196,7 @@ class OracleEnv(object):
         return xf.calc_heading(xf.quaternion_multiply(rot, inv_def))
 
     # ---- reset (quadruped_gym_env.py:63-104, minitaur.py:232-278, imitation_task.py:166-199) ----
-    def reset(self, mask=None, draws=None):
+    def reset(self, mask=None, draws=None, time_offset=None):
         N, s = self.N, self.spec
         m = np.ones(N, dtype=bool) if mask is None else np.asarray(mask, dtype=bool)
         mm = m[:, None]
@@ -232,6 +232,8 @@ class OracleEnv(object):
         self.clip = np.where(m, clip, self.clip)                                 # :701
         dur = self.lib.duration[self.clip]
         off = np.where(self.warmup, 0 + (self.task["warmup_time"] - 0) * u_time, 0 + (dur - 0) * u_time)  # :1103-1123
+        if time_offset is not None:      # replay of recorded reference draws (tests): exact offset instead of dur * u
+            off = np.asarray(time_offset, dtype=np.float64)
         self.time_offset = np.where(m, off, self.time_offset)
         self.episode = np.where(m, self.episode + 1, self.episode)
         # _reset_ref_motion :694-732

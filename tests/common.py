@@ -108,3 +108,18 @@ def random_states(rng, n, robot="laikago"):
     pose = np.concatenate([pos, quat, q], axis=1).astype(np.float32)
     vel = np.concatenate([rng.normal(size=(n, 3)), rng.normal(size=(n, 3)) * 2, rng.normal(size=(n, 12)) * 3], axis=1).astype(np.float32)
     return pose, vel
+
+
+def sync_product_from_oracle_reset(env, orc):
+    """Load the state of a freshly reset OracleEnv into the CUDA env (replay of recorded reference draws)."""
+    N = orc.N
+    f32 = lambda a: np.asarray(a, dtype=np.float32)
+    st = dict(pos=f32(orc.pos), quat=f32(orc.quat), q=f32(orc.q), lin=f32(orc.lin), ang=f32(orc.ang), qd=f32(orc.qd),
+              filt_x=f32(orc.filt_x), filt_y=f32(orc.filt_y), prev_filtered=f32(orc.prev_filtered),
+              ring1=f32(orc.hist[:, 1, 0:12]), ring2=f32(orc.hist[:, 1, 0:12]),
+              imu_hist=f32(orc.imu_hist), act_hist=f32(orc.act_hist), ang_hist=f32(orc.ang_hist),
+              ref_pose=f32(orc.ref_pose), ref_vel=f32(orc.ref_vel), origin_pos=f32(orc.origin_pos), origin_rot=f32(orc.origin_rot),
+              time_offset=orc.time_offset.copy(), prev_phase=orc.prev_phase.copy(), clip=orc.clip.astype(np.int32),
+              warmup=orc.warmup.astype(np.int32), substep_counter=np.zeros(N, np.int32), step_counter=np.zeros(N, np.int32),
+              env_step_counter=np.zeros(N, np.int32), obs_quat=np.tile(np.array([0, 0, 0, 1], np.float32), (N, 1)))
+    env.set_state(st)

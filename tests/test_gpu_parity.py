@@ -329,3 +329,29 @@ def test_policy_rollout_statistics():
     assert np.abs(rs[:5] - ros[:5]).max() < 5e-3            # short horizon: still the same trajectory
     assert abs(rs.mean() - ros.mean()) < 0.02
     env.close()
+
+
+@pytest.mark.parametrize("robot,clip", [("laikago", "laikago_pace"), ("laikago", "laikago_spin"), ("mini_cheetah", "minicheetah_trot")])
+def test_cuda_path_against_reference_class_trace(robot, clip):
+    """tests/golden/ref_task_trace.npz was produced by the reference's own Minitaur/ImitationTask/LocomotionGymEnv/
+    WrapperEnv code (scripts/make_trace.py).  The CUDA env replays the recorded reset draws and actions; trajectories
+    are chaotic over a rollout, so the comparison is tight on the first steps and statistical afterwards."""
+    TR = np.load(common.GOLD + "/ref_task_trace.npz")
+    n = len(TR[clip + "/clip"])
+    env = common.make_product(robot, [clip], n)
+    orc = common.make_oracle(robot, [clip], n, phys=common.oracle_phys_from_product(env.phys))
+    orc.reset(draws=(TR[clip + "/u_rsi"], TR[clip + "/clip"], np.zeros(n)), time_offset=TR[clip + "/time_offset"])
+    env.reset()
+    common.sync_product_from_oracle_reset(env, orc)
+    ref_obs, ref_rew, ref_done = TR[clip + "/obs"], TR[clip + "/reward"], TR[clip + "/done"]
+    rews = []
+    for t, a in enumerate(TR[clip + "/action"]):
+        o, r, d = env.step(torch.as_tensor(a.astype(np.float32), device=env.device))
+        o, r, d = o.cpu().numpy(), r.cpu().numpy(), d.cpu().numpy().astype(bool)
+        rews.append(r)
+        if t < 4:
+            assert np.abs(o - ref_obs[t + 1]).max() < 5e-3 and np.abs(r - ref_rew[t]).max() < 1e-3, t
+            assert np.array_equal(d, ref_done[t])
+    rews = np.array(rews)
+    assert abs(rews.mean() - ref_rew.mean()) < 0.03
+    env.close()
