@@ -54,6 +54,7 @@ def test_matches_tensor_env_and_episode_semantics(motion_file):
     assert env._max_episode_steps == 20                                   # curriculum start (run.py:54, wrapper_env.py:151-159)
     ten = common.make_product("laikago", ["laikago_pace"], n, seed=7, max_episode_steps=20)
     o = env.reset()
+    ten.reset_host()       # LocomotionGymEnv.__init__ already reset once (quadruped_gym_env.py:211): episode index 1
     np.testing.assert_array_equal(np.array(o, dtype=np.float32), ten.reset_host())
     rng = np.random.default_rng(0)
     count0 = env._total_step_count
