@@ -210,6 +210,16 @@ int orl_forward_dynamics(orl_env* env, const float* pose_dev, const float* vel_d
 int orl_reward_terms(orl_env* env, float* terms_dev, void* stream);
 /* Number of kernels this handle has launched since creation (bench.py "gpu_launches"). */
 int64_t orl_launch_count(const orl_env* env);
+/* ---- next row: rollout post-processing on the device -------------------------- */
+/* Per-robot GAE(lambda) over the runner's time-major interleaved buffers (index t*N + j), replacing
+ * add_vtarg_and_adv (R/agents/ppo_imitation.py:68-93) and the per-robot advantage standardisation
+ * (ppo_imitation.py:329-338).  reference_index_quirk != 0 reproduces the reference's non-terminal lookup
+ * episode_starts[(t*N + i) + (1 + i)] (:88) instead of episode_starts[(t+1)*N + i]; out-of-range reads are
+ * "not a start" like the reference's [False]*num_robot padding.  standardize != 0 applies (adv - mean_t)/std_t
+ * per robot (population std) AFTER tdlamret = adv + vpred has been formed.  No env handle: pure function. */
+int orl_gae(const float* rewards_dev, const float* vpred_dev, const float* nextvpred_dev,
+            const uint8_t* episode_starts_dev, int32_t T, int32_t N, float gamma, float lam,
+            int32_t reference_index_quirk, int32_t standardize, float* adv_dev, float* tdlamret_dev, void* stream);
 /* Measurement helper (no reference counterpart): sustained FP32 FFMA throughput of `device` in TFLOP/s,
  * the denominator of the FP32-pipe roofline (the driver measures no FP32 figure). */
 int orl_fp32_peak(int32_t device, int32_t repeats, double* tflops_out);

@@ -99,6 +99,7 @@ SYMBOLS = {
     "orl_reward_terms": (C.c_int, [_P, _P, _P]),
     "orl_launch_count": (C.c_int64, [_P]),
     "orl_fp32_peak": (C.c_int, [C.c_int32, C.c_int32, _P]),
+    "orl_gae": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_int32, C.c_int32, _P, _P, _P]),
 }
 
 # ORL_LIB lets experiments load an alternative build of the same library (kernel-variant A/B runs)

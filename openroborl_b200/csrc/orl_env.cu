@@ -589,3 +589,39 @@ extern "C" int orl_fp32_peak(int32_t device, int32_t repeats, double* tflops_out
   *tflops_out = best;
   return ORL_OK;
 }
+
+// ---- GAE(lambda) over the interleaved rollout buffers (ppo_imitation.py:68-93, 329-338) -------------------
+__global__ void orl_gae_kernel(const float* __restrict__ rew, const float* __restrict__ vpred, const float* __restrict__ nextv,
+                               const uint8_t* __restrict__ es, int T, int N, float gamma, float lam, int quirk, int standardize,
+                               float* __restrict__ adv, float* __restrict__ ret) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  float last = 0.f;
+  double sum = 0.0, sum2 = 0.0;
+  for (int t = T - 1; t >= 0; --t) {
+    const long idx = (long)t * N + i;
+    const long e = quirk ? idx + 1 + i : idx + N;
+    const float nonterminal = 1.0f - ((e < (long)T * N) ? (float)(es[e] != 0) : 0.0f);
+    const float delta = rew[idx] + gamma * nextv[idx] - vpred[idx];
+    last = delta + gamma * lam * nonterminal * last;
+    adv[idx] = last;
+    ret[idx] = last + vpred[idx];
+    sum += last; sum2 += (double)last * last;
+  }
+  if (standardize) {
+    const double mean = sum / T;
+    const double var = fmax(sum2 / T - mean * mean, 0.0);
+    const float m = (float)mean, inv = (float)(1.0 / sqrt(var));
+    for (int t = 0; t < T; ++t) { const long idx = (long)t * N + i; adv[idx] = (adv[idx] - m) * inv; }
+  }
+}
+
+extern "C" int orl_gae(const float* rewards_dev, const float* vpred_dev, const float* nextvpred_dev, const uint8_t* episode_starts_dev,
+                       int32_t T, int32_t N, float gamma, float lam, int32_t reference_index_quirk, int32_t standardize,
+                       float* adv_dev, float* tdlamret_dev, void* stream) {
+  if (!rewards_dev || !vpred_dev || !nextvpred_dev || !episode_starts_dev || !adv_dev || !tdlamret_dev || T <= 0 || N <= 0)
+    return ORL_ERR_INVALID;
+  orl_gae_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(rewards_dev, vpred_dev, nextvpred_dev, episode_starts_dev, T, N,
+                                                                  gamma, lam, reference_index_quirk, standardize, adv_dev, tdlamret_dev);
+  return cudaGetLastError() == cudaSuccess ? ORL_OK : ORL_ERR_CUDA;
+}

@@ -87,7 +87,8 @@ def policies(ref):
         z = zipfile.ZipFile(os.path.join(pdir, name + ".zip"))
         p = np.load(io.BytesIO(z.read("parameters")))
         data = json.loads(z.read("data"))
-        out = {k: p["model/%s:0" % k] for k in ("pi_fc0/w", "pi_fc0/b", "pi_fc1/w", "pi_fc1/b", "pi/w", "pi/b")}
+        out = {k: p["model/%s:0" % k] for k in ("pi_fc0/w", "pi_fc0/b", "pi_fc1/w", "pi_fc1/b", "pi/w", "pi/b",
+                                                 "vf_fc0/w", "vf_fc0/b", "vf_fc1/w", "vf_fc1/b", "vf/w", "vf/b")}
         try:
             box = _Unpickler(io.BytesIO(base64.b64decode(data["observation_space"][":serialized:"]))).load()
             out["obs_low"], out["obs_high"] = np.asarray(box.low), np.asarray(box.high)
