@@ -21,8 +21,9 @@ struct __align__(16) DevCp {
 struct __align__(16) DevLeg {
   DevJoint j[3];
   float4 ee[2];        // end-effector link COM xyz, body (int bits)
-  int4 meta;           // n_ee, base bounding radius (float bits), max margin of non-foot points (float bits), unused
+  int4 meta;           // n_ee, base bounding radius (float bits), max margin of non-foot points (float bits), primary cp index
   int4 cnt;            // collision points on body 0, 1, 2 and on the base share; stored in that order in cp[]
+  float4 bb[4][2];     // per body (0,1,2,base): body-frame bounding box of its NON-primary points: (centre xyz, max radius), (half extents, -)
   DevCp cp[ORL_MAX_CP];
 };
 struct __align__(16) DevModel {

@@ -125,10 +125,37 @@ static void pack_model(const orl_robot_model& m, DevModel& d) {
         if (c.body != body) continue;
         D.cp[pos].a = make_float4(c.local[0], c.local[1], c.local[2], c.radius);
         D.cp[pos].b = make_float4(c.mu, c.margin, f_from_i(c.is_foot ? 1 : 0), 0.f);
-        const float r = sqrtf(c.local[0] * c.local[0] + c.local[1] * c.local[1] + c.local[2] * c.local[2]) + c.radius;
-        if (r > brad[g]) brad[g] = r;
         if (!c.is_foot && c.margin > mmax) mmax = c.margin;
         ++pos; ++cnt[g];
+      }
+    }
+    // primary contact point: the foot-link sphere on body 2 with the largest radius (the toe)
+    int prim = -1; float prad = 0.f;
+    for (int i = cnt[0] + cnt[1]; i < cnt[0] + cnt[1] + cnt[2]; ++i)
+      if (i_from_f(D.cp[i].b.z) != 0 && D.cp[i].a.w > prad) { prad = D.cp[i].a.w; prim = i; }
+    // bounds of every body's collision points WITHOUT the primary point (it is evaluated unconditionally):
+    // bounding radius about the body origin, and the body-frame bounding box used for the per-substep test
+    // "can any point of this body be below the ground?" (lowest possible z = c.z' - sum h_i |R_zi| - rmax)
+    {
+      const int first[4] = {0, cnt[0], cnt[0] + cnt[1], cnt[0] + cnt[1] + cnt[2]};
+      for (int g = 0; g < 4; ++g) {
+        float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f}, rmax = 0.f;
+        int n = 0;
+        for (int i = first[g]; i < first[g] + cnt[g]; ++i) {
+          if (i == prim) continue;
+          const float4 a = D.cp[i].a;
+          const float xyz[3] = {a.x, a.y, a.z};
+          for (int k = 0; k < 3; ++k) { lo[k] = fminf(lo[k], xyz[k]); hi[k] = fmaxf(hi[k], xyz[k]); }
+          rmax = fmaxf(rmax, a.w);
+          const float r = sqrtf(a.x * a.x + a.y * a.y + a.z * a.z) + a.w;
+          if (r > brad[g]) brad[g] = r;
+          ++n;
+        }
+        if (n == 0) { D.bb[g][0] = make_float4(0.f, 0.f, 0.f, -1e30f); D.bb[g][1] = make_float4(0.f, 0.f, 0.f, 0.f); }
+        else {
+          D.bb[g][0] = make_float4(0.5f * (lo[0] + hi[0]), 0.5f * (lo[1] + hi[1]), 0.5f * (lo[2] + hi[2]), rmax);
+          D.bb[g][1] = make_float4(0.5f * (hi[0] - lo[0]), 0.5f * (hi[1] - lo[1]), 0.5f * (hi[2] - lo[2]), 0.f);
+        }
       }
     }
     for (int k = 0; k < 3; ++k) {
@@ -144,7 +171,7 @@ static void pack_model(const orl_robot_model& m, DevModel& d) {
     }
     for (int e = 0; e < 2; ++e)
       D.ee[e] = make_float4(L.ee_local[e][0], L.ee_local[e][1], L.ee_local[e][2], f_from_i(L.ee_body[e]));
-    D.meta = make_int4(L.n_ee, i_from_f(brad[3]), i_from_f(mmax), 0);
+    D.meta = make_int4(L.n_ee, i_from_f(brad[3]), i_from_f(mmax), prim);
     D.cnt = make_int4(cnt[0], cnt[1], cnt[2], cnt[3]);
   }
   d.n_links = m.n_links;
@@ -193,8 +220,8 @@ extern "C" int orl_create(const orl_config* cfg, const orl_robot_model* model, o
     pack_model(*model, packed);
     CUDA_TRY(e, cudaMemcpy(e->d_model, &packed, sizeof(DevModel), cudaMemcpyHostToDevice));
   }
-  CUDA_TRY(e, cudaMalloc(&e->d_stats, 4 * sizeof(double)));
-  CUDA_TRY(e, cudaMemset(e->d_stats, 0, 4 * sizeof(double)));
+  CUDA_TRY(e, cudaMalloc(&e->d_stats, 8 * sizeof(double)));
+  CUDA_TRY(e, cudaMemset(e->d_stats, 0, 8 * sizeof(double)));
   // motor strengths default to 1, orientation of the control observation to identity
   {
     std::vector<float> init(nstate, 0.f);
@@ -501,7 +528,11 @@ extern "C" int orl_stats(orl_env* e, double out[4], int32_t reset_after) {
   CUDA_TRY(e, cudaSetDevice(e->device));
   CUDA_TRY(e, cudaDeviceSynchronize());
   CUDA_TRY(e, cudaMemcpy(out, e->d_stats, 4 * sizeof(double), cudaMemcpyDeviceToHost));
-  if (reset_after) CUDA_TRY(e, cudaMemset(e->d_stats, 0, 4 * sizeof(double)));
+#ifdef ORL_DEBUG_COUNTERS
+  { double dbg[8]; cudaMemcpy(dbg, e->d_stats, 8 * sizeof(double), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[orl debug] warp-steps %.0f  switched-to-full %.0f  substeps-in-full %.0f\n", dbg[4], dbg[5], dbg[6]); }
+#endif
+  if (reset_after) CUDA_TRY(e, cudaMemset(e->d_stats, 0, 8 * sizeof(double)));
   return ORL_OK;
 }
 

@@ -212,6 +212,77 @@ ORL_DI void reset_robot(float* S, const DevEnv& E, const DevModel& Mo, int gid, 
   __syncwarp(qmask);
 }
 
+// Per-lane state advanced by the physics substeps, and the per-step constants of the action path.
+struct LaneDyn {
+  float3 pos, lin, ang;
+  Q4 quat;
+  float q[3], qd[3];
+  float r1[3], r2[3];         // true motor angles one / two substeps ago (control latency ring)
+  Q4 obs_q; float3 obs_w;     // control observation captured two substeps before the end of the step
+};
+struct LaneCtl {
+  float target[3], prevf[3], strength[3];
+  float dir[3], off[3], kp[3], kd[3], lo[3], up[3], damp[3];
+  float mac, inv_ar;
+  Q4 init_inv;
+  int capture;
+  bool first_step;
+};
+
+// One 1 ms physics substep of this lane's leg (+ the redundantly integrated base).
+ORL_DI void substep(const DevLeg& L, const DevModel& Mo, const PhysParams& P, const LaneCtl& Ctl, LaneDyn& D, int s) {
+  const M3 Rb = qmat(D.quat);
+  LegFK K;
+  leg_fk<true>(L, Rb, D.q, K);
+  const unsigned cmask = leg_contact_mask(L, K, Rb, D.pos.z);
+  const float lerp = (float)(s + 1) * Ctl.inv_ar;
+  float tau[3], qm_now[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float qobs = wrap_pi_fast(D.r2[k]);                              // get_motor_angles(): delayed + wrapped
+    const float prev = Ctl.first_step ? qobs : Ctl.prevf[k];               // minitaur.py:450-453
+    float cmd = fmaf(lerp, Ctl.target[k] - prev, prev);                    // :455-456
+    cmd = fminf(fmaxf(cmd, qobs - Ctl.mac), qobs + Ctl.mac);               // :706-723
+    const float qm = (D.q[k] - Ctl.off[k]) * Ctl.dir[k];                   // :549-553
+    const float qdm = D.qd[k] * Ctl.dir[k];                                // :575-578
+    const float tm = Ctl.strength[k] * (-1.0f * (Ctl.kp[k] * (qm - cmd)) - Ctl.kd[k] * qdm);   // minitaur_motor.py:163-166
+    const float e = fmaxf(0.f, Ctl.lo[k] - D.q[k]) - fmaxf(0.f, D.q[k] - Ctl.up[k]);
+    tau[k] = fmaf(tm, Ctl.dir[k], fmaf(P.klim, e, -(fmaf(P.dlim, fminf(1.0f, fabsf(e) * P.inv_e0), Ctl.damp[k])) * D.qd[k]));
+    qm_now[k] = qm;
+  }
+  float3 alpha, alin; float qdd[3];
+  leg_dynamics<true, false>(L, Mo, P, K, cmask, Rb, D.pos.z, D.ang, D.lin, D.q, D.qd, tau, alpha, alin, qdd, nullptr);
+  // semi-implicit Euler: velocities first, then positions with the new velocities
+  const float3 lin_dot = cross_add(D.ang, D.lin, alin);
+  D.ang = fma3(P.dt, alpha, D.ang);
+  D.lin = fma3(P.dt, lin_dot, D.lin);
+  D.pos = fma3(P.dt, D.lin, D.pos);
+  {
+    // quaternion exponential of w*dt: sin(h)/|w| and cos(h), h = |w| dt / 2 (Taylor series while h < 0.05)
+    const float w2 = dot(D.ang, D.ang);
+    const float h2 = 0.25f * P.dt * P.dt * w2;
+    float kk = 0.5f * P.dt * fmaf(h2, fmaf(h2, 1.0f / 120.0f, -1.0f / 6.0f), 1.0f);
+    float ch = fmaf(h2, fmaf(h2, 1.0f / 24.0f, -0.5f), 1.0f);
+    if (h2 >= 2.5e-3f) {
+      const float iw = rsqrtf(w2);
+      float sh;
+      __sincosf(0.5f * w2 * iw * P.dt, &sh, &ch);
+      kk = sh * iw;
+    }
+    D.quat = qnormalize(qmul(q4(D.ang.x * kk, D.ang.y * kk, D.ang.z * kk, ch), D.quat));
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    D.qd[k] = fmaf(P.dt, qdd[k], D.qd[k]);
+    D.q[k] = fmaf(P.dt, D.qd[k], D.q[k]);
+    D.r2[k] = D.r1[k]; D.r1[k] = qm_now[k];
+  }
+  if (s == Ctl.capture) {   // the control observation at the end of the step is 2 substeps old (minitaur.py:336-357)
+    D.obs_q = qmul(D.quat, Ctl.init_inv);                              // :325-331
+    D.obs_w = qrot(qconj(D.obs_q), D.ang);                             // :652-672
+  }
+}
+
 // =================================================================================================
 // The fused control step (WrapperEnv.step): SURVEY.md A.3 steps 1-7.
 // =================================================================================================
@@ -259,62 +330,29 @@ __global__ void __launch_bounds__(32, ORL_STEP_MIN_BLOCKS) orl_step_kernel(DevEn
     target[k] = y;
   }
   // 2. physics substeps (quadruped_gym_env.py:220-225)
-  Q4 obs_q = ldq(S + S_OBSQ);
-  float3 obs_w = v3(0.f, 0.f, 0.f);
-  const Q4 init_inv = qconj(ldq4(Mo->iquat));
-  const float mac = Mo->b1.w;
-  const int AR = C.action_repeat;
-  const float inv_ar = 1.0f / (float)AR;
-  for (int s = 0; s < AR; ++s) {
-    const float lerp = (float)(s + 1) * inv_ar;
-    const M3 Rb = qmat(quat);
-    float tau[3], qm_now[3];
+  // The loop body is kept below the SM's 32 KB instruction cache (one warp per scheduler cannot hide fetch
+  // misses): single copy of the contact code, rolled exact tests, SFU trigonometry (profiles/r01_v3_step_kernel.md).
+  LaneDyn D;
+  D.pos = pos; D.quat = quat; D.lin = lin; D.ang = ang;
+  D.obs_q = ldq(S + S_OBSQ); D.obs_w = v3(0.f, 0.f, 0.f);
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const float qobs = wrap_pi_fast(r2[k]);                          // get_motor_angles(): delayed + wrapped
-      const float prev = first_step ? qobs : prevf[k];                 // minitaur.py:450-453
-      float cmd = fmaf(lerp, target[k] - prev, prev);                  // :455-456
-      cmd = fminf(fmaxf(cmd, qobs - mac), qobs + mac);                 // :706-723
-      const float qm = (q[k] - j_off[k]) * j_dir[k];                   // :549-553
-      const float qdm = qd[k] * j_dir[k];                              // :575-578
-      const float tm = strength[k] * (-1.0f * (j_kp[k] * (qm - cmd)) - j_kd[k] * qdm);     // minitaur_motor.py:163-166
-      const float e = fmaxf(0.f, j_lo[k] - q[k]) - fmaxf(0.f, q[k] - j_up[k]);
-      tau[k] = fmaf(tm, j_dir[k], fmaf(P.klim, e, -(fmaf(P.dlim, fminf(1.0f, fabsf(e) * P.inv_e0), j_damp[k])) * qd[k]));
-      qm_now[k] = qm;
-    }
-    float3 alpha, alin; float qdd[3];
-    leg_dynamics<true, false, true>(L, *Mo, P, Rb, pos.z, ang, lin, q, qd, tau, alpha, alin, qdd, nullptr);
-    // semi-implicit Euler: velocities first, then positions with the new velocities
-    const float3 lin_dot = cross_add(ang, lin, alin);
-    ang = fma3(P.dt, alpha, ang);
-    lin = fma3(P.dt, lin_dot, lin);
-    pos = fma3(P.dt, lin, pos);
-    {
-      // quaternion exponential of w*dt: sin(h)/|w| and cos(h), h = |w| dt / 2, by Taylor series while h < 0.05
-      const float h2 = 0.25f * P.dt * P.dt * dot(ang, ang);
-      float kk, ch;
-      if (h2 < 2.5e-3f) {
-        kk = 0.5f * P.dt * fmaf(h2, fmaf(h2, 1.0f / 120.0f, -1.0f / 6.0f), 1.0f);
-        ch = fmaf(h2, fmaf(h2, 1.0f / 24.0f, -0.5f), 1.0f);
-      } else {
-        const float wn = sqrtf(dot(ang, ang));
-        float sh;
-        sincosf(0.5f * wn * P.dt, &sh, &ch);
-        kk = sh / wn;
-      }
-      quat = qnormalize(qmul(q4(ang.x * kk, ang.y * kk, ang.z * kk, ch), quat));
-    }
+  for (int k = 0; k < 3; ++k) { D.q[k] = q[k]; D.qd[k] = qd[k]; D.r1[k] = r1[k]; D.r2[k] = r2[k]; }
+  LaneCtl Ctl;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      qd[k] = fmaf(P.dt, qdd[k], qd[k]);
-      q[k] = fmaf(P.dt, qd[k], q[k]);
-      r2[k] = r1[k]; r1[k] = qm_now[k];
-    }
-    if (s == AR - 3) {   // the control observation at the end of the step is 2 substeps old (minitaur.py:336-357)
-      obs_q = qmul(quat, init_inv);                                    // :325-331
-      obs_w = qrot(qconj(obs_q), ang);                                 // :652-672
-    }
+  for (int k = 0; k < 3; ++k) {
+    Ctl.target[k] = target[k]; Ctl.prevf[k] = prevf[k]; Ctl.strength[k] = strength[k];
+    Ctl.dir[k] = j_dir[k]; Ctl.off[k] = j_off[k]; Ctl.kp[k] = j_kp[k]; Ctl.kd[k] = j_kd[k];
+    Ctl.lo[k] = j_lo[k]; Ctl.up[k] = j_up[k]; Ctl.damp[k] = j_damp[k];
   }
+  Ctl.first_step = first_step; Ctl.mac = Mo->b1.w; Ctl.init_inv = qconj(ldq4(Mo->iquat));
+  const int AR = C.action_repeat;
+  Ctl.inv_ar = 1.0f / (float)AR; Ctl.capture = AR - 3;
+  for (int s = 0; s < AR; ++s) substep(L, *Mo, P, Ctl, D, s);
+  pos = D.pos; quat = D.quat; lin = D.lin; ang = D.ang;
+  const Q4 obs_q = D.obs_q;
+  const float3 obs_w = D.obs_w;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { q[k] = D.q[k]; qd[k] = D.qd[k]; r1[k] = D.r1[k]; r2[k] = D.r2[k]; }
   // ---- write the dynamic state back to the record ---------------------------------------------------
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
@@ -547,8 +585,10 @@ __global__ void orl_dyn_kernel(const DevModel* Mo, PhysParams P, int mode, const
   const M3 Rb = qmat(ldq(p + 3));
   float3 alpha, alin; float qdd[3];
   DynExport ex;
-  if (mode == 2) leg_dynamics<true, false, false>(L, *Mo, P, Rb, p[2], ang, lin, q, qd, tau, alpha, alin, qdd, nullptr);
-  else leg_dynamics<false, true, false>(L, *Mo, P, Rb, p[2], ang, lin, q, qd, tau, alpha, alin, qdd, &ex);
+  LegFK K;
+  leg_fk<false>(L, Rb, q, K);
+  if (mode == 2) leg_dynamics<true, false>(L, *Mo, P, K, leg_contact_mask(L, K, Rb, p[2]), Rb, p[2], ang, lin, q, qd, tau, alpha, alin, qdd, nullptr);
+  else leg_dynamics<false, true>(L, *Mo, P, K, 0u, Rb, p[2], ang, lin, q, qd, tau, alpha, alin, qdd, &ex);
   if (mode == 2) {
     if (!valid) return;
     float* o = out + (size_t)i * 18;

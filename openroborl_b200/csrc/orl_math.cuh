@@ -116,7 +116,9 @@ ORL_DI float wrap_pi(float a) {
   return m;
 }
 // identical to wrap_pi, without the fmodf loop in the (usual) case |a| < pi
-ORL_DI float wrap_pi_fast(float a) { return fabsf(a) < ORL_PI_F ? a : wrap_pi(a); }
+// Compact variant for the substep loop (code size): identical to wrap_pi for |a| < pi; beyond, the nearest-
+// multiple reduction differs from it only at a = pi + 2 pi k exactly (maps to +pi instead of -pi).
+ORL_DI float wrap_pi_fast(float a) { return fabsf(a) < ORL_PI_F ? a : fmaf(-ORL_TWO_PI_F, rintf(a * (1.0f / ORL_TWO_PI_F)), a); }
 // pybullet.getEulerFromQuaternion (roll, pitch only) and yaw
 ORL_DI void bullet_euler(Q4 q, float& roll, float& pitch, float& yaw) {
   float sqx = q.x * q.x, sqy = q.y * q.y, sqz = q.z * q.z, squ = q.w * q.w;
