@@ -158,6 +158,7 @@ static void pack_model(const orl_robot_model& m, DevModel& d) {
         }
       }
     }
+    for (int i = pos; i < ORL_MAX_CP; ++i) D.cp[i].a = make_float4(0.f, 0.f, 0.f, -1e30f);   // unused slots never penetrate
     for (int k = 0; k < 3; ++k) {
       DevJoint& J = D.j[k];
       J.r0 = make_float4(L.R_fix[k][0], L.R_fix[k][1], L.R_fix[k][2], L.p_fix[k][0]);
