@@ -212,25 +212,26 @@ ORL_DI void reset_robot(float* S, const DevEnv& E, const DevModel& Mo, int gid, 
   __syncwarp(qmask);
 }
 
-// Per-lane state advanced by the physics substeps, and the per-step constants of the action path.
+// Per-lane state advanced by the physics substeps, and the per-step values of the action path.  Everything that
+// is constant over the step and cheap to re-read (joint/motor constants in the shared-memory model, motor
+// strengths in the staged record) is NOT kept here: the substep loop is register bound (255) and every
+// loop-invariant register costs a spill in the hot path (profiles/r01_v3_step_kernel.md).
 struct LaneDyn {
   float3 pos, lin, ang;
   Q4 quat;
   float q[3], qd[3];
   float r1[3], r2[3];         // true motor angles one / two substeps ago (control latency ring)
-  Q4 obs_q; float3 obs_w;     // control observation captured two substeps before the end of the step
 };
 struct LaneCtl {
-  float target[3], prevf[3], strength[3];
-  float dir[3], off[3], kp[3], kd[3], lo[3], up[3], damp[3];
+  float target[3], prevf[3];
   float mac, inv_ar;
-  Q4 init_inv;
   int capture;
   bool first_step;
 };
+#define S_OBSW 37           // scratch in the record's padding: body-frame angular velocity of the control observation
 
 // One 1 ms physics substep of this lane's leg (+ the redundantly integrated base).
-ORL_DI void substep(const DevLeg& L, const DevModel& Mo, const PhysParams& P, const LaneCtl& Ctl, LaneDyn& D, int s) {
+ORL_DI void substep(const DevLeg& L, const DevModel& Mo, const PhysParams& P, const LaneCtl& Ctl, LaneDyn& D, float* S, int s) {
   const M3 Rb = qmat(D.quat);
   LegFK K;
   leg_fk<true>(L, Rb, D.q, K);
@@ -239,15 +240,17 @@ ORL_DI void substep(const DevLeg& L, const DevModel& Mo, const PhysParams& P, co
   float tau[3], qm_now[3];
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
+    const float4 c1 = L.j[k].c1, m0 = L.j[k].m0, m1 = L.j[k].m1;   // (comy comz lower upper) (damping dir offset kp) (kd init motor brad)
+    const float strength = S[S_STRENGTH + __float_as_int(m1.z)];
     const float qobs = wrap_pi_fast(D.r2[k]);                              // get_motor_angles(): delayed + wrapped
     const float prev = Ctl.first_step ? qobs : Ctl.prevf[k];               // minitaur.py:450-453
     float cmd = fmaf(lerp, Ctl.target[k] - prev, prev);                    // :455-456
     cmd = fminf(fmaxf(cmd, qobs - Ctl.mac), qobs + Ctl.mac);               // :706-723
-    const float qm = (D.q[k] - Ctl.off[k]) * Ctl.dir[k];                   // :549-553
-    const float qdm = D.qd[k] * Ctl.dir[k];                                // :575-578
-    const float tm = Ctl.strength[k] * (-1.0f * (Ctl.kp[k] * (qm - cmd)) - Ctl.kd[k] * qdm);   // minitaur_motor.py:163-166
-    const float e = fmaxf(0.f, Ctl.lo[k] - D.q[k]) - fmaxf(0.f, D.q[k] - Ctl.up[k]);
-    tau[k] = fmaf(tm, Ctl.dir[k], fmaf(P.klim, e, -(fmaf(P.dlim, fminf(1.0f, fabsf(e) * P.inv_e0), Ctl.damp[k])) * D.qd[k]));
+    const float qm = (D.q[k] - m0.z) * m0.y;                               // :549-553
+    const float qdm = D.qd[k] * m0.y;                                      // :575-578
+    const float tm = strength * (-1.0f * (m0.w * (qm - cmd)) - m1.x * qdm);   // minitaur_motor.py:163-166
+    const float e = fmaxf(0.f, c1.z - D.q[k]) - fmaxf(0.f, D.q[k] - c1.w);
+    tau[k] = fmaf(tm, m0.y, fmaf(P.klim, e, -(fmaf(P.dlim, fminf(1.0f, fabsf(e) * P.inv_e0), m0.x)) * D.qd[k]));
     qm_now[k] = qm;
   }
   float3 alpha, alin; float qdd[3];
@@ -278,8 +281,9 @@ ORL_DI void substep(const DevLeg& L, const DevModel& Mo, const PhysParams& P, co
     D.r2[k] = D.r1[k]; D.r1[k] = qm_now[k];
   }
   if (s == Ctl.capture) {   // the control observation at the end of the step is 2 substeps old (minitaur.py:336-357)
-    D.obs_q = qmul(D.quat, Ctl.init_inv);                              // :325-331
-    D.obs_w = qrot(qconj(D.obs_q), D.ang);                             // :652-672
+    const Q4 oq = qmul(D.quat, qconj(ldq4(Mo.iquat)));                 // :325-331
+    const float3 ow = qrot(qconj(oq), D.ang);                          // :652-672
+    stq(S + S_OBSQ, oq); st3(S + S_OBSW, ow);                          // identical in the four lanes of the quad
   }
 }
 
@@ -307,21 +311,19 @@ __global__ void __launch_bounds__(32, ORL_STEP_MIN_BLOCKS) orl_step_kernel(DevEn
   // ---- registers -----------------------------------------------------------------------------
   float3 pos = ld3(S + S_POS), lin = ld3(S + S_LIN), ang = ld3(S + S_ANG);
   Q4 quat = ldq(S + S_QUAT);
-  float q[3], qd[3], target[3], act[3], prevf[3], r1[3], r2[3], strength[3];
+  float q[3], qd[3], target[3], act[3], prevf[3], r1[3], r2[3];
   int mi[3];
-  float j_dir[3], j_off[3], j_kp[3], j_kd[3], j_lo[3], j_up[3], j_damp[3];
   const int substep0 = as_int(S[S_SUBSTEP]);
   const bool first_step = as_int(S[S_STEP]) == 0;
   // 1. set_act: a += INIT; Butterworth (minitaur.py:280-285, 1169-1178; action_filter.py:111-127)
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
-    const float4 c1 = L.j[k].c1, m0 = L.j[k].m0, m1 = L.j[k].m1;
+    const float4 m1 = L.j[k].m1;
     const int m = __float_as_int(m1.z);
     mi[k] = m;
-    j_lo[k] = c1.z; j_up[k] = c1.w; j_damp[k] = m0.x; j_dir[k] = m0.y; j_off[k] = m0.z; j_kp[k] = m0.w; j_kd[k] = m1.x;
     q[k] = S[S_Q + 3 * leg + k]; qd[k] = S[S_QD + 3 * leg + k];
     r1[k] = S[S_RING1 + m]; r2[k] = S[S_RING2 + m];
-    prevf[k] = S[S_PREV + m]; strength[k] = S[S_STRENGTH + m];
+    prevf[k] = S[S_PREV + m];
     act[k] = __ldg(actions + (size_t)robot_c * 12 + m) + m1.y;
     float x0 = S[S_FX + m], x1 = S[S_FX + 12 + m], y0 = S[S_FY + m], y1 = S[S_FY + 12 + m];
     if (substep0 == 0) { const float d = wrap_pi_fast(r2[k]); x0 = x1 = y0 = y1 = d; }
@@ -334,23 +336,20 @@ __global__ void __launch_bounds__(32, ORL_STEP_MIN_BLOCKS) orl_step_kernel(DevEn
   // misses): single copy of the contact code, rolled exact tests, SFU trigonometry (profiles/r01_v3_step_kernel.md).
   LaneDyn D;
   D.pos = pos; D.quat = quat; D.lin = lin; D.ang = ang;
-  D.obs_q = ldq(S + S_OBSQ); D.obs_w = v3(0.f, 0.f, 0.f);
 #pragma unroll
   for (int k = 0; k < 3; ++k) { D.q[k] = q[k]; D.qd[k] = qd[k]; D.r1[k] = r1[k]; D.r2[k] = r2[k]; }
   LaneCtl Ctl;
 #pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    Ctl.target[k] = target[k]; Ctl.prevf[k] = prevf[k]; Ctl.strength[k] = strength[k];
-    Ctl.dir[k] = j_dir[k]; Ctl.off[k] = j_off[k]; Ctl.kp[k] = j_kp[k]; Ctl.kd[k] = j_kd[k];
-    Ctl.lo[k] = j_lo[k]; Ctl.up[k] = j_up[k]; Ctl.damp[k] = j_damp[k];
-  }
-  Ctl.first_step = first_step; Ctl.mac = Mo->b1.w; Ctl.init_inv = qconj(ldq4(Mo->iquat));
+  for (int k = 0; k < 3; ++k) { Ctl.target[k] = target[k]; Ctl.prevf[k] = prevf[k]; }
+  Ctl.first_step = first_step; Ctl.mac = Mo->b1.w;
   const int AR = C.action_repeat;
   Ctl.inv_ar = 1.0f / (float)AR; Ctl.capture = AR - 3;
-  for (int s = 0; s < AR; ++s) substep(L, *Mo, P, Ctl, D, s);
+  __syncwarp();
+  for (int s = 0; s < AR; ++s) substep(L, *Mo, P, Ctl, D, S, s);
+  __syncwarp();
   pos = D.pos; quat = D.quat; lin = D.lin; ang = D.ang;
-  const Q4 obs_q = D.obs_q;
-  const float3 obs_w = D.obs_w;
+  const Q4 obs_q = ldq(S + S_OBSQ);
+  const float3 obs_w = ld3(S + S_OBSW);
 #pragma unroll
   for (int k = 0; k < 3; ++k) { q[k] = D.q[k]; qd[k] = D.qd[k]; r1[k] = D.r1[k]; r2[k] = D.r2[k]; }
   // ---- write the dynamic state back to the record ---------------------------------------------------
