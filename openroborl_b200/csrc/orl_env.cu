@@ -426,6 +426,7 @@ static int check_launch(orl_env* e, const char* what) {
 extern "C" int orl_reset(orl_env* e, const uint8_t* mask_dev, float* obs_dev, void* stream) {
   NEED_MOTIONS(e);
   const int blocks = (e->cfg.num_robot + ORL_ROBOTS_PER_WARP - 1) / ORL_ROBOTS_PER_WARP;
+  if ((uintptr_t)obs_dev & 15) return fail(e, ORL_ERR_INVALID, "observation buffer must be 16-byte aligned");
   orl_reset_kernel<<<blocks, 32, ORL_SMEM_BYTES, (cudaStream_t)stream>>>(e->dev, mask_dev, obs_dev);
   return check_launch(e, "orl_reset_kernel");
 }
@@ -433,6 +434,7 @@ extern "C" int orl_reset(orl_env* e, const uint8_t* mask_dev, float* obs_dev, vo
 extern "C" int orl_step(orl_env* e, const float* actions_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev, void* stream) {
   NEED_MOTIONS(e);
   if (!actions_dev || !obs_dev || !reward_dev || !done_dev) return fail(e, ORL_ERR_INVALID, "null buffer");
+  if ((uintptr_t)obs_dev & 15) return fail(e, ORL_ERR_INVALID, "observation buffer must be 16-byte aligned");
   const int blocks = (e->cfg.num_robot + ORL_ROBOTS_PER_WARP - 1) / ORL_ROBOTS_PER_WARP;
   orl_step_kernel<<<blocks, 32, ORL_SMEM_BYTES, (cudaStream_t)stream>>>(e->dev, actions_dev, obs_dev, reward_dev, done_dev);
   return check_launch(e, "orl_step_kernel");
@@ -529,10 +531,6 @@ extern "C" int orl_stats(orl_env* e, double out[4], int32_t reset_after) {
   CUDA_TRY(e, cudaSetDevice(e->device));
   CUDA_TRY(e, cudaDeviceSynchronize());
   CUDA_TRY(e, cudaMemcpy(out, e->d_stats, 4 * sizeof(double), cudaMemcpyDeviceToHost));
-#ifdef ORL_DEBUG_COUNTERS
-  { double dbg[8]; cudaMemcpy(dbg, e->d_stats, 8 * sizeof(double), cudaMemcpyDeviceToHost);
-    fprintf(stderr, "[orl debug] warp-steps %.0f  switched-to-full %.0f  substeps-in-full %.0f\n", dbg[4], dbg[5], dbg[6]); }
-#endif
   if (reset_after) CUDA_TRY(e, cudaMemset(e->d_stats, 0, 8 * sizeof(double)));
   return ORL_OK;
 }

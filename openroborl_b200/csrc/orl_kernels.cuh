@@ -36,50 +36,63 @@ struct DevEnv {
 };
 
 #define ORL_SMEM_MODEL_BYTES ((sizeof(DevModel) + 15) / 16 * 16)
-#define ORL_SMEM_BYTES (ORL_SMEM_MODEL_BYTES + ORL_ROBOTS_PER_WARP * (ORL_STRIDE + ORL_OBS_SIZE) * 4)
+#define ORL_SMEM_BAR_OFFSET (ORL_SMEM_MODEL_BYTES + ORL_ROBOTS_PER_WARP * (ORL_STRIDE + ORL_OBS_SIZE) * 4)
+#define ORL_SMEM_BYTES (ORL_SMEM_BAR_OFFSET + 16)      // + one mbarrier
 
 ORL_DI int& as_int(float& f) { return *reinterpret_cast<int*>(&f); }
 ORL_DI double ld_f64(const float* p) { return *reinterpret_cast<const double*>(p); }
 ORL_DI void st_f64(float* p, double v) { *reinterpret_cast<double*>(p) = v; }
 
 // ---- shared-memory staging ---------------------------------------------------------------------
+// One thread block = one warp = 8 robots.  The packed model (same bytes for every block, L2 resident) and the
+// warp's 8 contiguous state records are fetched with two TMA bulk copies (cp.async.bulk, SASS UBLKCP) that
+// complete on one mbarrier: one round trip to L2/HBM instead of ~30 dependent LDG->STS iterations per lane.
+ORL_DI uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+ORL_DI void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+ORL_DI void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(dst), "r"(src), "r"(bytes) : "memory");
+}
 ORL_DI void stage_in(const DevEnv& E, unsigned char* smem, const DevModel*& Mo, float*& st, float*& ob) {
   const int lane = threadIdx.x;
-  float4* m4 = reinterpret_cast<float4*>(smem);
-  const float4* g4 = reinterpret_cast<const float4*>(E.model);
-  for (int i = lane; i < (int)(ORL_SMEM_MODEL_BYTES / 16); i += 32) m4[i] = g4[i];
   Mo = reinterpret_cast<const DevModel*>(smem);
   st = reinterpret_cast<float*>(smem + ORL_SMEM_MODEL_BYTES);
   ob = st + ORL_ROBOTS_PER_WARP * ORL_STRIDE;
   const int row0 = blockIdx.x * ORL_ROBOTS_PER_WARP;
-  const int R4 = ORL_STRIDE / 4;
-  const float4* s4 = reinterpret_cast<const float4*>(E.state);
-  float4* d4 = reinterpret_cast<float4*>(st);
-  for (int i = lane; i < ORL_ROBOTS_PER_WARP * R4; i += 32) {
-    const int row = min(row0 + i / R4, E.cfg.n - 1);
-    d4[i] = s4[(size_t)row * R4 + (i % R4)];
+  const int nrow = min(ORL_ROBOTS_PER_WARP, E.cfg.n - row0);
+  const uint32_t bar = smem_addr(smem + ORL_SMEM_BAR_OFFSET);
+  if (lane == 0) {
+    const uint32_t sbytes = (uint32_t)nrow * ORL_STRIDE * 4u;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"((uint32_t)ORL_SMEM_MODEL_BYTES + sbytes) : "memory");
+    bulk_g2s(smem_addr(st), E.state + (size_t)row0 * ORL_STRIDE, sbytes, bar);
+    bulk_g2s(smem_addr(smem), E.model, (uint32_t)ORL_SMEM_MODEL_BYTES, bar);
   }
   __syncwarp();
+  uint32_t ready = 0;
+  while (!ready)
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ready) : "r"(bar) : "memory");
+  if (nrow < ORL_ROBOTS_PER_WARP) {        // last block: idle quads work on a copy of the last valid record
+    for (int i = lane; i < (ORL_ROBOTS_PER_WARP - nrow) * ORL_STRIDE; i += 32)
+      st[nrow * ORL_STRIDE + i] = st[(nrow - 1) * ORL_STRIDE + i % ORL_STRIDE];
+    __syncwarp();
+  }
 }
 ORL_DI void stage_out(const DevEnv& E, const float* st, const float* ob, float* obs_out) {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to the bulk copy
   __syncwarp();
-  const int lane = threadIdx.x;
-  const int row0 = blockIdx.x * ORL_ROBOTS_PER_WARP;
-  const int R4 = ORL_STRIDE / 4;
-  float4* s4 = reinterpret_cast<float4*>(E.state);
-  const float4* d4 = reinterpret_cast<const float4*>(st);
-  for (int i = lane; i < ORL_ROBOTS_PER_WARP * R4; i += 32) {
-    const int row = row0 + i / R4;
-    if (row < E.cfg.n) s4[(size_t)row * R4 + (i % R4)] = d4[i];
-  }
-  if (obs_out) {
-    const int O4 = ORL_OBS_SIZE / 4;
-    float4* o4 = reinterpret_cast<float4*>(obs_out);
-    const float4* b4 = reinterpret_cast<const float4*>(ob);
-    for (int i = lane; i < ORL_ROBOTS_PER_WARP * O4; i += 32) {
-      const int row = row0 + i / O4;
-      if (row < E.cfg.n) o4[(size_t)row * O4 + (i % O4)] = b4[i];
-    }
+  if (threadIdx.x == 0) {
+    const int row0 = blockIdx.x * ORL_ROBOTS_PER_WARP;
+    const int nrow = min(ORL_ROBOTS_PER_WARP, E.cfg.n - row0);
+    bulk_s2g(E.state + (size_t)row0 * ORL_STRIDE, smem_addr(st), (uint32_t)nrow * ORL_STRIDE * 4u);
+    if (obs_out) bulk_s2g(obs_out + (size_t)row0 * ORL_OBS_SIZE, smem_addr(ob), (uint32_t)nrow * ORL_OBS_SIZE * 4u);
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   }
 }
 
