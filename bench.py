@@ -168,8 +168,11 @@ def run_ours(args):
     total_ms = float(sum(step_ms))
     st = env.stats(reset=True)
     # ---- end to end through the host-buffer C-ABI call -------------------------------------------------
-    acts = [b.cpu().numpy() for b in bank]
-    out = (np.empty((N, 160), np.float32), np.empty(N, np.float32), np.empty(N, np.uint8))
+    acts = []
+    for b in bank:                          # every step's actions start in page-locked host memory
+        a, out = env.alloc_host_buffers()
+        a[...] = b.cpu().numpy()
+        acts.append(a)
     for i in range(3):
         env.step_host(acts[i % 16], out)
     barrier()
@@ -208,7 +211,7 @@ def run_ours(args):
                        "actions": "16 device-resident [N,12] tensors cycled", "episodes_finished_in_timed_region": st[2],
                        "mean_reward": st[0] / max(st[3], 1.0)},
             "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": N * 12 * 4, "d2h_bytes_per_step": N * (160 * 4 + 4 + 1),
-                    "steps": Ke, "api": "orl_step_host (C ABI, host buffers)"},
+                    "steps": Ke, "api": "orl_step_host (C ABI, page-locked host buffers)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp32", "achieved": ach_tf, "peak": tf.value, "unit": "TFLOP/s", "frac": ach_tf / tf.value if tf.value else None,
                          "traffic": None, "kernel": "orl_step_kernel", "flop_per_robot_step": FLOP_PER_ROBOT_STEP,

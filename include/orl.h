@@ -170,7 +170,9 @@ int orl_reset(orl_env* env, const uint8_t* mask_dev, float* obs_dev, void* strea
  * obs_dev [N][160], reward_dev [N], done_dev [N]. */
 int orl_step(orl_env* env, const float* actions_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev,
              void* stream);
-/* Same through HOST buffers (what the list-based reference API needs): H2D, step, D2H, synchronise. */
+/* Same through HOST buffers (what the list-based reference API needs): H2D, step, D2H, synchronise.
+ * Page-locked buffers (cudaMallocHost / cudaHostRegister) are used for DMA directly; pageable ones go through
+ * the library's pinned staging area in overlapped chunks.  obs_dev of orl_reset/orl_step must be 16-byte aligned. */
 int orl_reset_host(orl_env* env, const uint8_t* mask, float* obs);
 int orl_step_host(orl_env* env, const float* actions, float* obs, float* reward, uint8_t* done);
 

@@ -13,6 +13,7 @@
 #include "../../include/orl.h"
 #include "orl_kernels.cuh"
 
+#define ORL_D2H_CHUNKS 4
 struct orl_env {
   orl_config cfg;
   orl_robot_model model;
@@ -33,6 +34,7 @@ struct orl_env {
   float* p_act; float* p_obs; float* p_rew; uint8_t* p_done; uint8_t* p_mask;
   float* d_act; float* d_obs; float* d_rew; uint8_t* d_done; uint8_t* d_mask;
   cudaStream_t stream;
+  cudaEvent_t ev_chunk[ORL_D2H_CHUNKS];
 };
 
 static int fail(orl_env* e, int code, const char* fmt, ...) {
@@ -245,6 +247,7 @@ extern "C" int orl_create(const orl_config* cfg, const orl_robot_model* model, o
   CUDA_TRY(e, cudaMalloc(&e->d_done, (size_t)N));
   CUDA_TRY(e, cudaMalloc(&e->d_mask, (size_t)N));
   CUDA_TRY(e, cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  for (int i = 0; i < ORL_D2H_CHUNKS; ++i) CUDA_TRY(e, cudaEventCreateWithFlags(&e->ev_chunk[i], cudaEventDisableTiming));
   CUDA_TRY(e, cudaFuncSetAttribute(orl_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ORL_SMEM_BYTES));
   CUDA_TRY(e, cudaFuncSetAttribute(orl_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ORL_SMEM_BYTES));
   e->dev.state = e->d_state; e->dev.model = e->d_model; e->dev.stats = e->d_stats;
@@ -265,6 +268,7 @@ extern "C" int orl_destroy(orl_env* e) {
   cudaFree(e->d_state); cudaFree(e->d_model); cudaFree(e->d_stats);
   cudaFreeHost(e->p_act); cudaFreeHost(e->p_obs); cudaFreeHost(e->p_rew); cudaFreeHost(e->p_done); cudaFreeHost(e->p_mask);
   cudaFree(e->d_act); cudaFree(e->d_obs); cudaFree(e->d_rew); cudaFree(e->d_done); cudaFree(e->d_mask);
+  for (int i = 0; i < ORL_D2H_CHUNKS; ++i) if (e->ev_chunk[i]) cudaEventDestroy(e->ev_chunk[i]);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
   return ORL_OK;
@@ -440,6 +444,36 @@ extern "C" int orl_step(orl_env* e, const float* actions_dev, float* obs_dev, fl
   return check_launch(e, "orl_step_kernel");
 }
 
+// True when the CUDA runtime can DMA to/from this host pointer directly (cudaMallocHost / cudaHostRegister /
+// torch pin_memory): such buffers skip the internal pinned staging copy.
+static bool host_ptr_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
+// Device -> host copy of `bytes`: direct when dst is pinned, else through the pinned staging buffer in chunks so
+// that the CPU memcpy of chunk k overlaps the DMA of chunk k+1.  The caller synchronises the stream afterwards
+// only in the direct case (the staged case has consumed every chunk on return).
+static int d2h(orl_env* e, void* dst, void* staging, const void* src, size_t bytes, bool direct) {
+  if (direct) { CUDA_TRY(e, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, e->stream)); return ORL_OK; }
+  const int NC = bytes >= (1u << 20) ? ORL_D2H_CHUNKS : 1;
+  const size_t chunk = ((bytes + NC - 1) / NC + 255) & ~(size_t)255;
+  int used = 0;
+  for (size_t off = 0; off < bytes; off += chunk, ++used) {
+    const size_t nb = bytes - off < chunk ? bytes - off : chunk;
+    CUDA_TRY(e, cudaMemcpyAsync((char*)staging + off, (const char*)src + off, nb, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(e, cudaEventRecord(e->ev_chunk[used], e->stream));
+  }
+  used = 0;
+  for (size_t off = 0; off < bytes; off += chunk, ++used) {
+    const size_t nb = bytes - off < chunk ? bytes - off : chunk;
+    CUDA_TRY(e, cudaEventSynchronize(e->ev_chunk[used]));
+    memcpy((char*)dst + off, (const char*)staging + off, nb);
+  }
+  return ORL_OK;
+}
+
 extern "C" int orl_reset_host(orl_env* e, const uint8_t* mask, float* obs) {
   NEED_MOTIONS(e);
   CUDA_TRY(e, cudaSetDevice(e->device));
@@ -450,9 +484,8 @@ extern "C" int orl_reset_host(orl_env* e, const uint8_t* mask, float* obs) {
   }
   int rc = orl_reset(e, mask ? e->d_mask : nullptr, e->d_obs, e->stream);
   if (rc) return rc;
-  CUDA_TRY(e, cudaMemcpyAsync(e->p_obs, e->d_obs, (size_t)N * ORL_OBS_SIZE * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  if (obs && (rc = d2h(e, obs, e->p_obs, e->d_obs, (size_t)N * ORL_OBS_SIZE * sizeof(float), host_ptr_pinned(obs)))) return rc;
   CUDA_TRY(e, cudaStreamSynchronize(e->stream));
-  if (obs) memcpy(obs, e->p_obs, (size_t)N * ORL_OBS_SIZE * sizeof(float));
   return ORL_OK;
 }
 
@@ -461,17 +494,37 @@ extern "C" int orl_step_host(orl_env* e, const float* actions, float* obs, float
   if (!actions || !obs || !reward || !done) return fail(e, ORL_ERR_INVALID, "null buffer");
   CUDA_TRY(e, cudaSetDevice(e->device));
   const int N = e->cfg.num_robot;
-  memcpy(e->p_act, actions, (size_t)N * 12 * sizeof(float));
-  CUDA_TRY(e, cudaMemcpyAsync(e->d_act, e->p_act, (size_t)N * 12 * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+  const size_t ab = (size_t)N * 12 * sizeof(float), ob = (size_t)N * ORL_OBS_SIZE * sizeof(float);
+  const bool pin_a = host_ptr_pinned(actions), pin_o = host_ptr_pinned(obs), pin_r = host_ptr_pinned(reward), pin_d = host_ptr_pinned(done);
+  if (pin_a && pin_o && pin_r && pin_d && !((uintptr_t)obs & 15)) {
+    // Zero-copy: every buffer is page-locked, so the step kernel reads the actions and writes observation / reward /
+    // done straight through the mapped host pointers.  The PCIe transfers then overlap the kernel's own tail
+    // (warps finish at different times) instead of being serialised behind it as separate copies.
+    void *da, *dob, *dr, *dd;
+    CUDA_TRY(e, cudaHostGetDevicePointer(&da, (void*)actions, 0));
+    CUDA_TRY(e, cudaHostGetDevicePointer(&dob, obs, 0));
+    CUDA_TRY(e, cudaHostGetDevicePointer(&dr, reward, 0));
+    CUDA_TRY(e, cudaHostGetDevicePointer(&dd, done, 0));
+    int rc0 = orl_step(e, (const float*)da, (float*)dob, (float*)dr, (uint8_t*)dd, e->stream);
+    if (rc0) return rc0;
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    return ORL_OK;
+  }
+  if (pin_a) {
+    CUDA_TRY(e, cudaMemcpyAsync(e->d_act, actions, ab, cudaMemcpyHostToDevice, e->stream));
+  } else {
+    memcpy(e->p_act, actions, ab);
+    CUDA_TRY(e, cudaMemcpyAsync(e->d_act, e->p_act, ab, cudaMemcpyHostToDevice, e->stream));
+  }
   int rc = orl_step(e, e->d_act, e->d_obs, e->d_rew, e->d_done, e->stream);
   if (rc) return rc;
-  CUDA_TRY(e, cudaMemcpyAsync(e->p_obs, e->d_obs, (size_t)N * ORL_OBS_SIZE * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
-  CUDA_TRY(e, cudaMemcpyAsync(e->p_rew, e->d_rew, (size_t)N * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
-  CUDA_TRY(e, cudaMemcpyAsync(e->p_done, e->d_done, (size_t)N, cudaMemcpyDeviceToHost, e->stream));
+  // small results first so that they ride along with the first observation chunk
+  CUDA_TRY(e, cudaMemcpyAsync(pin_r ? reward : e->p_rew, e->d_rew, (size_t)N * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(e, cudaMemcpyAsync(pin_d ? done : e->p_done, e->d_done, (size_t)N, cudaMemcpyDeviceToHost, e->stream));
+  if ((rc = d2h(e, obs, e->p_obs, e->d_obs, ob, pin_o))) return rc;
   CUDA_TRY(e, cudaStreamSynchronize(e->stream));
-  memcpy(obs, e->p_obs, (size_t)N * ORL_OBS_SIZE * sizeof(float));
-  memcpy(reward, e->p_rew, (size_t)N * sizeof(float));
-  memcpy(done, e->p_done, (size_t)N);
+  if (!pin_r) memcpy(reward, e->p_rew, (size_t)N * sizeof(float));
+  if (!pin_d) memcpy(done, e->p_done, (size_t)N);
   return ORL_OK;
 }
 

@@ -163,6 +163,17 @@ class BatchedImitationEnv(object):
         self._check(self._lib.orl_reset_host(self._h, mp, obs.ctypes.data))
         return obs
 
+    def alloc_host_buffers(self):
+        """Page-locked host buffers (actions, (obs, reward, done)) as NumPy views: `step_host` DMAs straight
+        from/to them; ordinary NumPy arrays work too but go through the library's pinned staging copy."""
+        t = [torch.empty((self.num_robot, _abi.NUM_MOTORS), dtype=torch.float32).pin_memory(),
+             torch.empty((self.num_robot, _abi.OBS_SIZE), dtype=torch.float32).pin_memory(),
+             torch.empty(self.num_robot, dtype=torch.float32).pin_memory(),
+             torch.empty(self.num_robot, dtype=torch.uint8).pin_memory()]
+        self._pinned = getattr(self, "_pinned", []) + t          # keep the allocations alive with the env
+        a, o, r, d = [x.numpy() for x in t]
+        return a, (o, r, d)
+
     def step_host(self, actions, out=None):
         actions = np.ascontiguousarray(actions, dtype=np.float32)
         if actions.shape != (self.num_robot, _abi.NUM_MOTORS):

@@ -269,6 +269,27 @@ def test_host_buffer_api_equals_device_api_and_ragged_sizes():
         a.close(); b.close(); big.close()
 
 
+def test_host_buffer_api_pinned_and_pageable_large_batch():
+    """orl_step_host: page-locked buffers (direct DMA) and pageable ones (chunked staging) give the same bytes."""
+    N = 8200                                      # > 1 MiB of observations: the chunked path; ragged last warp
+    a = common.make_product("laikago", ["laikago_pace"], N, seed=5)
+    b = common.make_product("laikago", ["laikago_pace"], N, seed=5)
+    c = common.make_product("laikago", ["laikago_pace"], N, seed=5)
+    pa, pout = b.alloc_host_buffers()
+    ref0 = a.reset().cpu().numpy()
+    assert np.array_equal(ref0, b.reset_host()) and np.array_equal(ref0, c.reset_host())
+    rng = np.random.default_rng(0)
+    for _ in range(3):
+        act = rng.normal(scale=0.1, size=(N, 12)).astype(np.float32)
+        o, r, d = a.step(torch.as_tensor(act, device=a.device))
+        pa[...] = act
+        op, rp, dp = b.step_host(pa, pout)
+        oh, rh, dh = c.step_host(act)
+        for x, y, z in ((o, op, oh), (r, rp, rh), (d, dp, dh)):
+            assert np.array_equal(x.cpu().numpy(), y) and np.array_equal(y, z)
+    a.close(); b.close(); c.close()
+
+
 def test_auto_reset_and_statistics():
     N = 512
     env = common.make_product("laikago", ["laikago_pace"], N, seed=1, auto_reset=True, max_episode_steps=5)
