@@ -6,6 +6,11 @@
 #include <stdint.h>
 #include "../../include/orl.h"
 
+// collision-point slots per leg on the device: the host's points grouped per body, each group padded to at least
+// ORL_CP_UNROLL entries; the penetration mask is one 32-bit word
+#define ORL_CP_UNROLL 3
+#define ORL_DEV_MAX_CP 32
+
 struct __align__(16) DevJoint {
   float4 r0, r1, r2;   // R_fix rows (xyz) + p_fix component (w)
   float4 i0;           // Ixx Ixy Ixz Iyy        (about the COM, body frame)
@@ -24,7 +29,7 @@ struct __align__(16) DevLeg {
   int4 meta;           // n_ee, base bounding radius (float bits), max margin of non-foot points (float bits), primary cp index
   int4 cnt;            // collision points on body 0, 1, 2 and on the base share; stored in that order in cp[]
   float4 bb[4][2];     // per body (0,1,2,base): body-frame bounding box of its NON-primary points: (centre xyz, max radius), (half extents, -)
-  DevCp cp[ORL_MAX_CP];
+  DevCp cp[ORL_DEV_MAX_CP];
 };
 struct __align__(16) DevModel {
   float4 b0;           // base mass, Ixx, Ixy, Ixz

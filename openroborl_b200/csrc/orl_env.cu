@@ -130,6 +130,13 @@ static void pack_model(const orl_robot_model& m, DevModel& d) {
         if (!c.is_foot && c.margin > mmax) mmax = c.margin;
         ++pos; ++cnt[g];
       }
+      // every group holds at least ORL_CP_UNROLL slots (body_contact_mask tests that many straight-line);
+      // padding entries can never penetrate (radius -1e30) and count as non-foot points with zero margin
+      while (cnt[g] < ORL_CP_UNROLL && pos < ORL_DEV_MAX_CP) {
+        D.cp[pos].a = make_float4(0.f, 0.f, 0.f, -1e30f);
+        D.cp[pos].b = make_float4(0.f, 0.f, f_from_i(0), 0.f);
+        ++pos; ++cnt[g];
+      }
     }
     // primary contact point: the foot-link sphere on body 2 with the largest radius (the toe)
     int prim = -1; float prad = 0.f;
@@ -144,7 +151,7 @@ static void pack_model(const orl_robot_model& m, DevModel& d) {
         float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f}, rmax = 0.f;
         int n = 0;
         for (int i = first[g]; i < first[g] + cnt[g]; ++i) {
-          if (i == prim) continue;
+          if (i == prim || D.cp[i].a.w < -1e29f) continue;
           const float4 a = D.cp[i].a;
           const float xyz[3] = {a.x, a.y, a.z};
           for (int k = 0; k < 3; ++k) { lo[k] = fminf(lo[k], xyz[k]); hi[k] = fmaxf(hi[k], xyz[k]); }
@@ -160,7 +167,7 @@ static void pack_model(const orl_robot_model& m, DevModel& d) {
         }
       }
     }
-    for (int i = pos; i < ORL_MAX_CP; ++i) D.cp[i].a = make_float4(0.f, 0.f, 0.f, -1e30f);   // unused slots never penetrate
+    for (int i = pos; i < ORL_DEV_MAX_CP; ++i) D.cp[i].a = make_float4(0.f, 0.f, 0.f, -1e30f);   // unused slots never penetrate
     for (int k = 0; k < 3; ++k) {
       DevJoint& J = D.j[k];
       J.r0 = make_float4(L.R_fix[k][0], L.R_fix[k][1], L.R_fix[k][2], L.p_fix[k][0]);
@@ -205,8 +212,14 @@ extern "C" int orl_create(const orl_config* cfg, const orl_robot_model* model, o
     if (model->leg[l].n_ee < 0 || model->leg[l].n_ee > 2) return fail(e, ORL_ERR_INVALID, "bad n_ee on leg %d", l);
     for (int k = 0; k < 3; ++k)
       if (model->leg[l].motor[k] < 0 || model->leg[l].motor[k] >= 12) return fail(e, ORL_ERR_INVALID, "bad motor index");
-    for (int i = 0; i < model->leg[l].n_cp; ++i)
+    int per_body[4] = {0, 0, 0, 0};
+    for (int i = 0; i < model->leg[l].n_cp; ++i) {
       if (model->leg[l].cp[i].body < -1 || model->leg[l].cp[i].body > 2) return fail(e, ORL_ERR_INVALID, "bad collision-point body");
+      ++per_body[model->leg[l].cp[i].body + 1];
+    }
+    int slots = 0;
+    for (int g = 0; g < 4; ++g) slots += per_body[g] < ORL_CP_UNROLL ? ORL_CP_UNROLL : per_body[g];
+    if (slots > ORL_DEV_MAX_CP) return fail(e, ORL_ERR_INVALID, "leg %d: collision points need %d device slots (max %d)", l, slots, ORL_DEV_MAX_CP);
     for (int i = 0; i < model->leg[l].n_ee; ++i)
       if (model->leg[l].ee_body[i] < 0 || model->leg[l].ee_body[i] > 2) return fail(e, ORL_ERR_INVALID, "bad end-effector body");
   }
@@ -429,9 +442,9 @@ static int check_launch(orl_env* e, const char* what) {
 
 extern "C" int orl_reset(orl_env* e, const uint8_t* mask_dev, float* obs_dev, void* stream) {
   NEED_MOTIONS(e);
-  const int blocks = (e->cfg.num_robot + ORL_ROBOTS_PER_WARP - 1) / ORL_ROBOTS_PER_WARP;
+  const int blocks = (e->cfg.num_robot + ORL_ROBOTS_PER_BLOCK - 1) / ORL_ROBOTS_PER_BLOCK;
   if ((uintptr_t)obs_dev & 15) return fail(e, ORL_ERR_INVALID, "observation buffer must be 16-byte aligned");
-  orl_reset_kernel<<<blocks, 32, ORL_SMEM_BYTES, (cudaStream_t)stream>>>(e->dev, mask_dev, obs_dev);
+  orl_reset_kernel<<<blocks, ORL_BLOCK_THREADS, ORL_SMEM_BYTES, (cudaStream_t)stream>>>(e->dev, mask_dev, obs_dev);
   return check_launch(e, "orl_reset_kernel");
 }
 
@@ -439,8 +452,8 @@ extern "C" int orl_step(orl_env* e, const float* actions_dev, float* obs_dev, fl
   NEED_MOTIONS(e);
   if (!actions_dev || !obs_dev || !reward_dev || !done_dev) return fail(e, ORL_ERR_INVALID, "null buffer");
   if ((uintptr_t)obs_dev & 15) return fail(e, ORL_ERR_INVALID, "observation buffer must be 16-byte aligned");
-  const int blocks = (e->cfg.num_robot + ORL_ROBOTS_PER_WARP - 1) / ORL_ROBOTS_PER_WARP;
-  orl_step_kernel<<<blocks, 32, ORL_SMEM_BYTES, (cudaStream_t)stream>>>(e->dev, actions_dev, obs_dev, reward_dev, done_dev);
+  const int blocks = (e->cfg.num_robot + ORL_ROBOTS_PER_BLOCK - 1) / ORL_ROBOTS_PER_BLOCK;
+  orl_step_kernel<<<blocks, ORL_BLOCK_THREADS, ORL_SMEM_BYTES, (cudaStream_t)stream>>>(e->dev, actions_dev, obs_dev, reward_dev, done_dev);
   return check_launch(e, "orl_step_kernel");
 }
 
@@ -609,7 +622,7 @@ static int dyn_call(orl_env* e, int mode, const float* pose, const float* vel, c
   if (!e) return ORL_ERR_INVALID;
   if (n <= 0) return ORL_OK;
   if (mode == 0) CUDA_TRY(e, cudaMemsetAsync(out, 0, (size_t)n * 324 * sizeof(float), (cudaStream_t)stream));
-  orl_dyn_kernel<<<(n * 4 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(e->d_model, e->dev.cfg.phys, mode, pose, vel, in, n, out);
+  orl_dyn_kernel<<<(n * 4 + ORL_DYN_BLOCK - 1) / ORL_DYN_BLOCK, ORL_DYN_BLOCK, 0, (cudaStream_t)stream>>>(e->d_model, e->dev.cfg.phys, mode, pose, vel, in, n, out);
   return check_launch(e, "orl_dyn_kernel");
 }
 extern "C" int orl_mass_matrix(orl_env* e, const float* pose_dev, int32_t n, float* M_dev, void* stream) {

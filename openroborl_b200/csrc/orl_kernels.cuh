@@ -35,9 +35,20 @@ struct DevEnv {
   double* stats;                      // [4]
 };
 
+// Thread block = ORL_WARPS_PER_BLOCK warps that run the substep loop in lockstep (one barrier per substep): the loop
+// body (~33 KB of SASS) is larger than the SM's 32 KB instruction cache, and warps of one block that stay within the
+// same code region share every fetched line instead of thrashing the cache at four different positions.
+#ifndef ORL_WARPS_PER_BLOCK
+#define ORL_WARPS_PER_BLOCK 4
+#endif
+#define ORL_BLOCK_THREADS (32 * ORL_WARPS_PER_BLOCK)
+#define ORL_ROBOTS_PER_BLOCK (ORL_ROBOTS_PER_WARP * ORL_WARPS_PER_BLOCK)
 #define ORL_SMEM_MODEL_BYTES ((sizeof(DevModel) + 15) / 16 * 16)
-#define ORL_SMEM_BAR_OFFSET (ORL_SMEM_MODEL_BYTES + ORL_ROBOTS_PER_WARP * (ORL_STRIDE + ORL_OBS_SIZE) * 4)
-#define ORL_SMEM_BYTES (ORL_SMEM_BAR_OFFSET + 16)      // + one mbarrier
+#define ORL_SMEM_OBS_BYTES (ORL_ROBOTS_PER_WARP * ORL_OBS_SIZE * 4)
+#define ORL_SMEM_X_BYTES (ORL_X_FLOAT4_PER_LANE * ORL_X_STRIDE * 16)
+#define ORL_SMEM_WARP_BYTES (ORL_ROBOTS_PER_WARP * ORL_STRIDE * 4 + (ORL_SMEM_X_BYTES > ORL_SMEM_OBS_BYTES ? ORL_SMEM_X_BYTES : ORL_SMEM_OBS_BYTES))
+#define ORL_SMEM_BAR_OFFSET (ORL_SMEM_MODEL_BYTES + ORL_WARPS_PER_BLOCK * ORL_SMEM_WARP_BYTES)
+#define ORL_SMEM_BYTES (ORL_SMEM_BAR_OFFSET + 8 * (ORL_WARPS_PER_BLOCK + 1) + 8)      // + one mbarrier per warp + one for the model
 
 ORL_DI int& as_int(float& f) { return *reinterpret_cast<int*>(&f); }
 ORL_DI double ld_f64(const float* p) { return *reinterpret_cast<const double*>(p); }
@@ -55,44 +66,60 @@ ORL_DI void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar
 ORL_DI void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(dst), "r"(src), "r"(bytes) : "memory");
 }
-ORL_DI void stage_in(const DevEnv& E, unsigned char* smem, const DevModel*& Mo, float*& st, float*& ob) {
-  const int lane = threadIdx.x;
-  Mo = reinterpret_cast<const DevModel*>(smem);
-  st = reinterpret_cast<float*>(smem + ORL_SMEM_MODEL_BYTES);
-  ob = st + ORL_ROBOTS_PER_WARP * ORL_STRIDE;
-  const int row0 = blockIdx.x * ORL_ROBOTS_PER_WARP;
-  const int nrow = min(ORL_ROBOTS_PER_WARP, E.cfg.n - row0);
-  const uint32_t bar = smem_addr(smem + ORL_SMEM_BAR_OFFSET);
-  if (lane == 0) {
-    const uint32_t sbytes = (uint32_t)nrow * ORL_STRIDE * 4u;
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"((uint32_t)ORL_SMEM_MODEL_BYTES + sbytes) : "memory");
-    bulk_g2s(smem_addr(st), E.state + (size_t)row0 * ORL_STRIDE, sbytes, bar);
-    bulk_g2s(smem_addr(smem), E.model, (uint32_t)ORL_SMEM_MODEL_BYTES, bar);
-  }
-  __syncwarp();
+ORL_DI void mbar_wait(uint32_t bar) {
   uint32_t ready = 0;
   while (!ready)
     asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
                  : "=r"(ready) : "r"(bar) : "memory");
-  if (nrow < ORL_ROBOTS_PER_WARP) {        // last block: idle quads work on a copy of the last valid record
-    for (int i = lane; i < (ORL_ROBOTS_PER_WARP - nrow) * ORL_STRIDE; i += 32)
-      st[nrow * ORL_STRIDE + i] = st[(nrow - 1) * ORL_STRIDE + i % ORL_STRIDE];
+}
+// First robot row of this warp and how many of its 8 rows exist (<= 0 for a warp past the end of the batch: it
+// runs on a copy of the last record to stay in the block's barriers and stores nothing).
+ORL_DI int warp_row0() { return (blockIdx.x * ORL_WARPS_PER_BLOCK + (threadIdx.x >> 5)) * ORL_ROBOTS_PER_WARP; }
+ORL_DI void stage_in(const DevEnv& E, unsigned char* smem, const DevModel*& Mo, float*& st, float*& ob) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  Mo = reinterpret_cast<const DevModel*>(smem);
+  st = reinterpret_cast<float*>(smem + ORL_SMEM_MODEL_BYTES + warp * ORL_SMEM_WARP_BYTES);
+  ob = st + ORL_ROBOTS_PER_WARP * ORL_STRIDE;
+  const int row0 = warp_row0();
+  const int nrow = min(ORL_ROBOTS_PER_WARP, E.cfg.n - row0);
+  const int src0 = nrow > 0 ? row0 : E.cfg.n - 1, nsrc = nrow > 0 ? nrow : 1;
+  const uint32_t bar_model = smem_addr(smem + ORL_SMEM_BAR_OFFSET), bar = bar_model + 8u * (warp + 1);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i <= ORL_WARPS_PER_BLOCK; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar_model + 8u * i) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  if (lane == 0) {
+    const uint32_t sbytes = (uint32_t)nsrc * ORL_STRIDE * 4u;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(sbytes) : "memory");
+    bulk_g2s(smem_addr(st), E.state + (size_t)src0 * ORL_STRIDE, sbytes, bar);
+    if (warp == 0) {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar_model), "r"((uint32_t)ORL_SMEM_MODEL_BYTES) : "memory");
+      bulk_g2s(smem_addr(smem), E.model, (uint32_t)ORL_SMEM_MODEL_BYTES, bar_model);
+    }
+  }
+  __syncwarp();
+  mbar_wait(bar);
+  mbar_wait(bar_model);
+  if (nsrc < ORL_ROBOTS_PER_WARP) {        // ragged end: idle quads work on a copy of the last valid record
+    for (int i = lane; i < (ORL_ROBOTS_PER_WARP - nsrc) * ORL_STRIDE; i += 32)
+      st[nsrc * ORL_STRIDE + i] = st[(nsrc - 1) * ORL_STRIDE + i % ORL_STRIDE];
     __syncwarp();
   }
 }
 ORL_DI void stage_out(const DevEnv& E, const float* st, const float* ob, float* obs_out) {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to the bulk copy
   __syncwarp();
-  if (threadIdx.x == 0) {
-    const int row0 = blockIdx.x * ORL_ROBOTS_PER_WARP;
+  if ((threadIdx.x & 31) == 0) {
+    const int row0 = warp_row0();
     const int nrow = min(ORL_ROBOTS_PER_WARP, E.cfg.n - row0);
-    bulk_s2g(E.state + (size_t)row0 * ORL_STRIDE, smem_addr(st), (uint32_t)nrow * ORL_STRIDE * 4u);
-    if (obs_out) bulk_s2g(obs_out + (size_t)row0 * ORL_OBS_SIZE, smem_addr(ob), (uint32_t)nrow * ORL_OBS_SIZE * 4u);
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    if (nrow > 0) {
+      bulk_s2g(E.state + (size_t)row0 * ORL_STRIDE, smem_addr(st), (uint32_t)nrow * ORL_STRIDE * 4u);
+      if (obs_out) bulk_s2g(obs_out + (size_t)row0 * ORL_OBS_SIZE, smem_addr(ob), (uint32_t)nrow * ORL_OBS_SIZE * 4u);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
   }
 }
 
@@ -244,11 +271,8 @@ struct LaneCtl {
 #define S_OBSW 37           // scratch in the record's padding: body-frame angular velocity of the control observation
 
 // One 1 ms physics substep of this lane's leg (+ the redundantly integrated base).
-ORL_DI void substep(const DevLeg& L, const DevModel& Mo, const PhysParams& P, const LaneCtl& Ctl, LaneDyn& D, float* S, int s) {
+ORL_DI void substep(const DevLeg& L, const DevModel& Mo, const PhysParams& P, const LaneCtl& Ctl, LaneDyn& D, float* S, float4* X, int s) {
   const M3 Rb = qmat(D.quat);
-  LegFK K;
-  leg_fk<true>(L, Rb, D.q, K);
-  const unsigned cmask = leg_contact_mask(L, K, Rb, D.pos.z);
   const float lerp = (float)(s + 1) * Ctl.inv_ar;
   float tau[3], qm_now[3];
 #pragma unroll
@@ -267,7 +291,7 @@ ORL_DI void substep(const DevLeg& L, const DevModel& Mo, const PhysParams& P, co
     qm_now[k] = qm;
   }
   float3 alpha, alin; float qdd[3];
-  leg_dynamics<true, false>(L, Mo, P, K, cmask, Rb, D.pos.z, D.ang, D.lin, D.q, D.qd, tau, alpha, alin, qdd, nullptr);
+  leg_dynamics<true, false, true>(L, Mo, P, Rb, D.pos.z, D.ang, D.lin, D.q, D.qd, tau, X, alpha, alin, qdd, nullptr);
   // semi-implicit Euler: velocities first, then positions with the new velocities
   const float3 lin_dot = cross_add(D.ang, D.lin, alin);
   D.ang = fma3(P.dt, alpha, D.ang);
@@ -304,20 +328,21 @@ ORL_DI void substep(const DevLeg& L, const DevModel& Mo, const PhysParams& P, co
 // The fused control step (WrapperEnv.step): SURVEY.md A.3 steps 1-7.
 // =================================================================================================
 #ifndef ORL_STEP_MIN_BLOCKS
-#define ORL_STEP_MIN_BLOCKS 8
+#define ORL_STEP_MIN_BLOCKS (8 / ORL_WARPS_PER_BLOCK)
 #endif
-__global__ void __launch_bounds__(32, ORL_STEP_MIN_BLOCKS) orl_step_kernel(DevEnv E, const float* __restrict__ actions, float* __restrict__ obs_out,
+__global__ void __launch_bounds__(ORL_BLOCK_THREADS, ORL_STEP_MIN_BLOCKS) orl_step_kernel(DevEnv E, const float* __restrict__ actions, float* __restrict__ obs_out,
                                                       float* __restrict__ reward_out, uint8_t* __restrict__ done_out) {
   extern __shared__ __align__(16) unsigned char smem[];
   const DevModel* Mo; float* st; float* ob;
   stage_in(E, smem, Mo, st, ob);
   const DevCfg& C = E.cfg;
-  const int lane = threadIdx.x, leg = lane & 3, rw = lane >> 2;
-  const int robot = blockIdx.x * ORL_ROBOTS_PER_WARP + rw;
+  const int lane = threadIdx.x & 31, leg = lane & 3, rw = lane >> 2;
+  const int robot = warp_row0() + rw;
   const bool valid = robot < C.n;
   const int robot_c = min(robot, C.n - 1);
   float* S = st + rw * ORL_STRIDE;
   float* O = ob + rw * ORL_OBS_SIZE;
+  float4* X = reinterpret_cast<float4*>(ob) + lane;      // dynamics scratch; aliases the observation staging (dead until build_obs)
   const DevLeg& L = Mo->leg[leg];
   const PhysParams P = C.phys;
 
@@ -358,7 +383,12 @@ __global__ void __launch_bounds__(32, ORL_STEP_MIN_BLOCKS) orl_step_kernel(DevEn
   const int AR = C.action_repeat;
   Ctl.inv_ar = 1.0f / (float)AR; Ctl.capture = AR - 3;
   __syncwarp();
-  for (int s = 0; s < AR; ++s) substep(L, *Mo, P, Ctl, D, S, s);
+  for (int s = 0; s < AR; ++s) {
+#if ORL_WARPS_PER_BLOCK > 1 && !defined(ORL_NO_LOCKSTEP)
+    __syncthreads();                       // keep the block's warps in the same code region (shared I-cache lines)
+#endif
+    substep(L, *Mo, P, Ctl, D, S, X, s);
+  }
   __syncwarp();
   pos = D.pos; quat = D.quat; lin = D.lin; ang = D.ang;
   const Q4 obs_q = ldq(S + S_OBSQ);
@@ -515,12 +545,12 @@ __global__ void __launch_bounds__(32, ORL_STEP_MIN_BLOCKS) orl_step_kernel(DevEn
 }
 
 // =================================================================================================
-__global__ void __launch_bounds__(32) orl_reset_kernel(DevEnv E, const uint8_t* __restrict__ mask, float* __restrict__ obs_out) {
+__global__ void __launch_bounds__(ORL_BLOCK_THREADS) orl_reset_kernel(DevEnv E, const uint8_t* __restrict__ mask, float* __restrict__ obs_out) {
   extern __shared__ __align__(16) unsigned char smem[];
   const DevModel* Mo; float* st; float* ob;
   stage_in(E, smem, Mo, st, ob);
-  const int lane = threadIdx.x, leg = lane & 3, rw = lane >> 2;
-  const int robot = blockIdx.x * ORL_ROBOTS_PER_WARP + rw;
+  const int lane = threadIdx.x & 31, leg = lane & 3, rw = lane >> 2;
+  const int robot = warp_row0() + rw;
   const int robot_c = min(robot, E.cfg.n - 1);
   float* S = st + rw * ORL_STRIDE;
   const bool doit = mask == nullptr || mask[robot_c] != 0;
@@ -576,6 +606,7 @@ __global__ void orl_fk_kernel(const DevModel* Mo, const float* pose, int n, floa
   }
 }
 
+#define ORL_DYN_BLOCK 64
 // mode 0: mass matrix [n][18][18]; 1: inverse dynamics tau [n][18]; 2: forward dynamics acc [n][18]
 // generalised velocity order of the interface: [lin(3), ang(3), joints(12)]
 __global__ void orl_dyn_kernel(const DevModel* Mo, PhysParams P, int mode, const float* pose, const float* vel,
@@ -597,10 +628,10 @@ __global__ void orl_dyn_kernel(const DevModel* Mo, PhysParams P, int mode, const
   const M3 Rb = qmat(ldq(p + 3));
   float3 alpha, alin; float qdd[3];
   DynExport ex;
-  LegFK K;
-  leg_fk<false>(L, Rb, q, K);
-  if (mode == 2) leg_dynamics<true, false>(L, *Mo, P, K, leg_contact_mask(L, K, Rb, p[2]), Rb, p[2], ang, lin, q, qd, tau, alpha, alin, qdd, nullptr);
-  else leg_dynamics<false, true>(L, *Mo, P, K, 0u, Rb, p[2], ang, lin, q, qd, tau, alpha, alin, qdd, &ex);
+  __shared__ float4 Xs[ORL_DYN_BLOCK / 32 * ORL_X_FLOAT4_PER_LANE * ORL_X_STRIDE];     // per-lane dynamics scratch
+  float4* X = Xs + (threadIdx.x >> 5) * (ORL_X_FLOAT4_PER_LANE * ORL_X_STRIDE) + (threadIdx.x & 31);
+  if (mode == 2) leg_dynamics<true, false, false>(L, *Mo, P, Rb, p[2], ang, lin, q, qd, tau, X, alpha, alin, qdd, nullptr);
+  else leg_dynamics<false, true, false>(L, *Mo, P, Rb, p[2], ang, lin, q, qd, tau, X, alpha, alin, qdd, &ex);
   if (mode == 2) {
     if (!valid) return;
     float* o = out + (size_t)i * 18;
