@@ -264,6 +264,7 @@ struct LaneDyn {
 };
 struct LaneCtl {
   float target[3], prevf[3];
+  float strength[3];
   float mac, inv_ar;
   int capture;
   bool first_step;
@@ -278,7 +279,7 @@ ORL_DI void substep(const DevLeg& L, const DevModel& Mo, const PhysParams& P, co
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     const float4 c1 = L.j[k].c1, m0 = L.j[k].m0, m1 = L.j[k].m1;   // (comy comz lower upper) (damping dir offset kp) (kd init motor brad)
-    const float strength = S[S_STRENGTH + __float_as_int(m1.z)];
+    const float strength = Ctl.strength[k];
     const float qobs = wrap_pi_fast(D.r2[k]);                              // get_motor_angles(): delayed + wrapped
     const float prev = Ctl.first_step ? qobs : Ctl.prevf[k];               // minitaur.py:450-453
     float cmd = fmaf(lerp, Ctl.target[k] - prev, prev);                    // :455-456
@@ -378,7 +379,7 @@ __global__ void __launch_bounds__(ORL_BLOCK_THREADS, ORL_STEP_MIN_BLOCKS) orl_st
   for (int k = 0; k < 3; ++k) { D.q[k] = q[k]; D.qd[k] = qd[k]; D.r1[k] = r1[k]; D.r2[k] = r2[k]; }
   LaneCtl Ctl;
 #pragma unroll
-  for (int k = 0; k < 3; ++k) { Ctl.target[k] = target[k]; Ctl.prevf[k] = prevf[k]; }
+  for (int k = 0; k < 3; ++k) { Ctl.target[k] = target[k]; Ctl.prevf[k] = prevf[k]; Ctl.strength[k] = S[S_STRENGTH + __float_as_int(L.j[k].m1.z)]; }
   Ctl.first_step = first_step; Ctl.mac = Mo->b1.w;
   const int AR = C.action_repeat;
   Ctl.inv_ar = 1.0f / (float)AR; Ctl.capture = AR - 3;

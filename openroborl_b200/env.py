@@ -47,7 +47,7 @@ class _DevView(object):
 
 class BatchedImitationEnv(object):
     def __init__(self, robot="laikago", motions=None, num_robot=1, device=0, seed=0, gid0=0, auto_reset=False,
-                 max_episode_steps=600, task=None, phys=None, urdf_search_path=None):
+                 max_episode_steps=600, task=None, phys=None, urdf_search_path=None, action_repeat=None):
         if not motions:
             raise ValueError("No reference motions specified.")           # imitation_task.py:583-584
         self._lib = _abi.load_library()
@@ -61,12 +61,14 @@ class BatchedImitationEnv(object):
         cfg = _abi.OrlConfig()
         cfg.abi_version = _abi.ORL_ABI_VERSION
         cfg.num_robot, cfg.device, cfg.gid0, cfg.seed = self.num_robot, int(device), int(gid0), int(seed)
-        cfg.action_repeat = spec.NUM_ACTION_REPEAT
+        # SimulationParameters.num_action_repeat (locomotion_gym_config.py); the robot classes fix it to 33
+        self.action_repeat = int(action_repeat or spec.NUM_ACTION_REPEAT)
+        cfg.action_repeat = self.action_repeat
         cfg.max_episode_steps = int(max_episode_steps)
         cfg.auto_reset = int(bool(auto_reset))
         cfg.enable_cycle_sync = int(bool(self.task["enable_cycle_sync"]))
         cfg.sim_time_step = spec.T_STEP
-        cfg.env_time_step = spec.NUM_ACTION_REPEAT * spec.T_STEP       # quadruped_gym_env.py:177
+        cfg.env_time_step = self.action_repeat * spec.T_STEP       # quadruped_gym_env.py:177
         cfg.warmup_time = self.task["warmup_time"]
         cfg.ref_state_init_prob = self.task["ref_state_init_prob"]
         if len(self.task["tar_frame_steps"]) != _abi.NUM_TAR_FRAMES:
