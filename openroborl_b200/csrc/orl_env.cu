@@ -597,6 +597,14 @@ extern "C" int orl_stats(orl_env* e, double out[4], int32_t reset_after) {
   CUDA_TRY(e, cudaSetDevice(e->device));
   CUDA_TRY(e, cudaDeviceSynchronize());
   CUDA_TRY(e, cudaMemcpy(out, e->d_stats, 4 * sizeof(double), cudaMemcpyDeviceToHost));
+#ifdef ORL_PROFILE_RARE
+  { unsigned long long h[24]; cudaMemcpyFromSymbol(h, orl_prof, sizeof(h));
+    fprintf(stderr, "[orl rare] entries %llu trips %llu cycles %llu | loop cycles %llu warp-steps %llu | max cycles %llu max trips %llu\n", h[0], h[1], h[2], h[3], h[4], h[5], h[6]);
+    fprintf(stderr, "[orl rare] cycles hist (8k buckets):"); for (int i = 0; i < 8; ++i) fprintf(stderr, " %llu", h[8 + i]);
+    fprintf(stderr, "\n[orl rare] trips hist (16 buckets):"); for (int i = 0; i < 8; ++i) fprintf(stderr, " %llu", h[16 + i]);
+    fprintf(stderr, "\n");
+    unsigned long long z[24] = {0}; cudaMemcpyToSymbol(orl_prof, z, sizeof(z)); }
+#endif
   if (reset_after) CUDA_TRY(e, cudaMemset(e->d_stats, 0, 8 * sizeof(double)));
   return ORL_OK;
 }

@@ -384,12 +384,28 @@ __global__ void __launch_bounds__(ORL_BLOCK_THREADS, ORL_STEP_MIN_BLOCKS) orl_st
   const int AR = C.action_repeat;
   Ctl.inv_ar = 1.0f / (float)AR; Ctl.capture = AR - 3;
   __syncwarp();
+#ifdef ORL_PROFILE_RARE
+  const long long tl0 = clock64();
+#endif
   for (int s = 0; s < AR; ++s) {
 #if ORL_WARPS_PER_BLOCK > 1 && !defined(ORL_NO_LOCKSTEP)
     __syncthreads();                       // keep the block's warps in the same code region (shared I-cache lines)
 #endif
     substep(L, *Mo, P, Ctl, D, S, X, s);
   }
+#ifdef ORL_PROFILE_RARE
+  if (lane == 0) {
+    atomicAdd(&orl_prof[3], (unsigned long long)(clock64() - tl0)); atomicAdd(&orl_prof[4], 1ull);
+    const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const unsigned long long rc = orl_prof_warp[0][gw], rt = orl_prof_warp[1][gw];
+    orl_prof_warp[0][gw] = 0; orl_prof_warp[1][gw] = 0;
+    int b = (int)(rc / 8192); if (b > 7) b = 7;
+    atomicAdd(&orl_prof[8 + b], 1ull);                    // histogram of rare cycles per warp-step, 8k-cycle buckets
+    int t = (int)(rt / 16); if (t > 7) t = 7;
+    atomicAdd(&orl_prof[16 + t], 1ull);                   // histogram of rare trips per warp-step, buckets of 16
+    atomicMax(&orl_prof[5], rc); atomicMax(&orl_prof[6], rt);
+  }
+#endif
   __syncwarp();
   pos = D.pos; quat = D.quat; lin = D.lin; ang = D.ang;
   const Q4 obs_q = ldq(S + S_OBSQ);
