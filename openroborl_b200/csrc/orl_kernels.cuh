@@ -439,7 +439,7 @@ __global__ void __launch_bounds__(ORL_BLOCK_THREADS, ORL_STEP_MIN_BLOCKS) orl_st
   // 4. reward against the reference state of the END of the previous step (imitation_task.py:341-516)
   const M3 Rb = qmat(quat);
   LegFK Ks, Kr;
-  leg_fk<false>(L, Rb, q, Ks);
+  leg_fk<true>(L, Rb, q, Ks);
   const float3 rp = ld3(S + S_REFPOSE);
   const Q4 rq = ldq(S + S_REFPOSE + 3);
   float rj[3];
@@ -450,12 +450,12 @@ __global__ void __launch_bounds__(ORL_BLOCK_THREADS, ORL_STEP_MIN_BLOCKS) orl_st
     const float dq = rj[k] - q[k], dv = S[S_REFVEL + 6 + 3 * leg + k] - qd[k];
     pose_err += dq * dq; vel_err += dv * dv;
   }
-  leg_fk<false>(L, qmat(rq), rj, Kr);
+  leg_fk<true>(L, qmat(rq), rj, Kr);
   {
     const Q4 inv_def = qconj(ldq4(Mo->iquat));                      // default root rotation, :1071-1075, 1245-1252
     float ss, cs, sr, cr;
-    sincosf(-qheading(qmul(quat, inv_def)), &ss, &cs);
-    sincosf(-qheading(qmul(rq, inv_def)), &sr, &cr);
+    qheading_neg_sincos(qmul(quat, inv_def), ss, cs);
+    qheading_neg_sincos(qmul(rq, inv_def), sr, cr);
     for (int e = 0; e < L.meta.x; ++e) {
       const float4 ee = L.ee[e];
       const int kb = __float_as_int(ee.w);
@@ -509,20 +509,22 @@ __global__ void __launch_bounds__(ORL_BLOCK_THREADS, ORL_STEP_MIN_BLOCKS) orl_st
   {
     const int4 cnt = L.cnt;
     const float mmax = __int_as_float(L.meta.z);          // largest margin of a non-foot point
-    const int first[4] = {0, cnt.x, cnt.x + cnt.y, cnt.x + cnt.y + cnt.z};
-    const int num[4] = {cnt.x, cnt.y, cnt.z, cnt.w};
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      const M3 Rk = b == 3 ? Rb : Ks.R[b == 3 ? 0 : b];
-      const float oz = pos.z + (b == 3 ? 0.f : Ks.p[b == 3 ? 0 : b].z);
+    int first = 0;
+#pragma unroll 1
+    for (int b = 0; b < 4; ++b) {          // rolled on purpose: once-per-step code is instruction-fetch bound
+      const float3 rz = b == 0 ? Ks.R[0].r2 : (b == 1 ? Ks.R[1].r2 : (b == 2 ? Ks.R[2].r2 : Rb.r2));
+      const float oz = pos.z + (b == 0 ? Ks.p[0].z : (b == 1 ? Ks.p[1].z : (b == 2 ? Ks.p[2].z : 0.f)));
       const float brad = b == 3 ? __int_as_float(L.meta.y) : L.j[b == 3 ? 0 : b].m1.w;
+      const int num = b == 0 ? cnt.x : (b == 1 ? cnt.y : (b == 2 ? cnt.z : cnt.w));
       if (oz < brad + mmax) {
-        for (int i = first[b]; i < first[b] + num[b]; ++i) {
+#pragma unroll 1
+        for (int i = first; i < first + num; ++i) {
           const float4 a = L.cp[i].a, bb = L.cp[i].b;
-          const float z = oz + dot(Rk.r2, f4xyz(a)) - a.w - bb.y;
+          const float z = oz + dot(rz, f4xyz(a)) - a.w - bb.y;
           fall |= (__float_as_int(bb.z) == 0) && (z < 0.f);
         }
       }
+      first += num;
     }
   }
   fall = quad_or(fall);      // Minitaur.step_counter > 0 always holds after a step (imitation_task.py:539)
@@ -728,8 +730,8 @@ __global__ void orl_reward_terms_kernel(DevEnv E, float* terms) {
   leg_fk<false>(L, qmat(rq), rj, Kr);
   const Q4 inv_def = qconj(ldq4(Mo->iquat));
   float ss, cs, sr, cr;
-  sincosf(-qheading(qmul(quat, inv_def)), &ss, &cs);
-  sincosf(-qheading(qmul(rq, inv_def)), &sr, &cr);
+  qheading_neg_sincos(qmul(quat, inv_def), ss, cs);
+  qheading_neg_sincos(qmul(rq, inv_def), sr, cr);
   for (int e = 0; e < L.meta.x; ++e) {
     const float4 ee = L.ee[e];
     const int kb = __float_as_int(ee.w);

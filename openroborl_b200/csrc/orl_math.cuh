@@ -99,6 +99,15 @@ ORL_DI float3 qrot_z(float s, float c, float3 v) {   // s = sin(angle), c = cos(
 ORL_DI float qheading(Q4 q) {
   return atan2f(2.f * (q.x * q.y + q.z * q.w), 1.f - 2.f * (q.y * q.y + q.z * q.z));
 }
+// sin / cos of MINUS the heading without trigonometry: the heading is atan2(y, x) of the rotated x axis, so
+// cos = x / |(x, y)| and sin = -y / |(x, y)| (heading 0 for a vertical axis, like atan2(0, 0))
+ORL_DI void qheading_neg_sincos(Q4 q, float& s, float& c) {
+  const float y = 2.f * (q.x * q.y + q.z * q.w), x = 1.f - 2.f * (q.y * q.y + q.z * q.z);
+  const float n2 = fmaf(x, x, y * y);
+  const float inv = n2 > 0.f ? rsqrtf(n2) : 0.f;
+  c = n2 > 0.f ? x * inv : 1.f;
+  s = -y * inv;
+}
 // pose3d.QuaternionToAxisAngle angle + normalize_rotation_angle
 ORL_DI float qangle_normalized(Q4 q) {
   float n = sqrtf(q.x * q.x + q.y * q.y + q.z * q.z);
