@@ -159,11 +159,9 @@ ORL_DI void build_obs(float* S, float* O, const DevEnv& E, int leg) {
   // robot.get_base_orientation(): delayed orientation -> euler -> quaternion (minitaur.py:513-527, 630-638)
   float roll, pitch, yaw;
   bullet_euler(ldq(S + S_OBSQ), roll, pitch, yaw);
-  const float heading = qheading(bullet_quat_from_euler(roll, pitch, yaw));
-  float sh, ch;
-  sincosf(-heading, &sh, &ch);
-  float shh, chh;
-  sincosf(-0.5f * heading, &shh, &chh);
+  float sh, ch, shh, chh;                     // sin / cos of -heading and of -heading / 2 (imitation_task.py:270-274)
+  qheading_neg_sincos(bullet_quat_from_euler(roll, pitch, yaw), sh, ch);
+  half_angle(sh, ch, shh, chh);
   const Q4 inv_rot = q4(0.f, 0.f, shh, chh);
   const double tt = __dadd_rn(t0, __dmul_rn((double)C.tar_steps[leg], C.env_dt));
   const RefSample s = ref_sample(E.mt, F, tt);
@@ -224,15 +222,15 @@ ORL_DI void reset_robot(float* S, const DevEnv& E, const DevModel& Mo, int gid, 
   if (warm) time = __dsub_rn(time, C.warmup_time);
   const RefSample s = ref_sample(E.mt, F, time);
   float3 p0; Q4 r0;
-  ref_root(E.mt, F, s, true, p0, r0);
+  ref_root_raw(E.mt, F, s, p0, r0);               // the origin is still the identity here
   const float3 sim_pos = f4xyz(Mo.ipos);
   const Q4 sim_rot = ldq4(Mo.iquat);
   float3 op = sim_pos - p0; op.z = 0.f;
   const float dh = qheading(sim_rot) - qheading(r0);
   F.origin_pos = op;
   F.origin_rot = qaxis_z(dh);
-  float3 rp, rl, ra3; Q4 rq;
-  ref_root(E.mt, F, s, true, rp, rq);
+  float3 rp = p0, rl, ra3; Q4 rq = r0;
+  ref_apply_origin(F, rp, rq);
   ref_root_vel(E.mt, F, s, rl, ra3);
   if (leg == 0) {
     st3(S + S_OPOS, F.origin_pos); stq(S + S_OROT, F.origin_rot);
@@ -484,14 +482,13 @@ __global__ void __launch_bounds__(ORL_BLOCK_THREADS, ORL_STEP_MIN_BLOCKS) orl_st
   const double time = motion_time(S, C);
   const double new_phase = motion_phase(E.mt, F.clip, time);
   const RefSample smp = ref_sample(E.mt, F, time);
+  float3 nrp, nrl, nra; Q4 nrq;
+  ref_root_raw(E.mt, F, smp, nrp, nrq);           // sampled once: the cycle-sync re-anchoring only moves the origin
   if (C.cycle_sync && new_phase < ld_f64(S + S_PPHASE)) {
-    float3 p0; Q4 r0;
-    ref_root(E.mt, F, smp, false, p0, r0);
-    float3 op = pos - qrot(F.origin_rot, p0); op.z = 0.f;
+    float3 op = pos - qrot(F.origin_rot, nrp); op.z = 0.f;
     F.origin_pos = op;
   }
-  float3 nrp, nrl, nra; Q4 nrq;
-  ref_root(E.mt, F, smp, true, nrp, nrq);
+  ref_apply_origin(F, nrp, nrq);
   ref_root_vel(E.mt, F, smp, nrl, nra);
   __syncwarp();
   if (leg == 0) {
@@ -592,14 +589,14 @@ __global__ void orl_motion_lookup_kernel(MotionTables T, const int32_t* clip, co
   if (blend) blend[i] = b.blend;
   if (pose) {
     float3 p; Q4 r;
-    motion_root(T, c, b, p, r);
+    motion_root(T, c, b, motion_cycle_offset(T, c, b.cycle), p, r);
     float* o = pose + (size_t)i * 19;
     st3(o, p); stq(o + 3, r);
     for (int j = 0; j < 12; ++j) o[7 + j] = motion_joint(T, c, b, j);
   }
   if (vel) {
     float3 l, a;
-    motion_root_vel(T, c, b, l, a);
+    motion_root_vel(T, c, b, motion_cycle_offset(T, c, b.cycle), l, a);
     float* o = vel + (size_t)i * 18;
     st3(o, l); st3(o + 3, a);
     for (int j = 0; j < 12; ++j) o[6 + j] = motion_joint_vel(T, c, b, j);

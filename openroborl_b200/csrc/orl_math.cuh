@@ -108,6 +108,12 @@ ORL_DI void qheading_neg_sincos(Q4 q, float& s, float& c) {
   c = n2 > 0.f ? x * inv : 1.f;
   s = -y * inv;
 }
+// half-angle of a rotation given by (s, c) = (sin a, cos a), a in (-pi, pi]: (sin a/2, cos a/2) without trigonometry;
+// each branch takes the square root of the well-conditioned one of (1 + c) / 2, (1 - c) / 2
+ORL_DI void half_angle(float s, float c, float& sh, float& ch) {
+  if (c >= 0.f) { ch = sqrtf(0.5f * (1.f + c)); sh = 0.5f * s / ch; }
+  else { const float a = sqrtf(0.5f * (1.f - c)); sh = s >= 0.f ? a : -a; ch = 0.5f * fabsf(s) / a; }
+}
 // pose3d.QuaternionToAxisAngle angle + normalize_rotation_angle
 ORL_DI float qangle_normalized(Q4 q) {
   float n = sqrtf(q.x * q.x + q.y * q.y + q.z * q.z);
@@ -142,8 +148,8 @@ ORL_DI void bullet_euler(Q4 q, float& roll, float& pitch, float& yaw) {
 }
 // pybullet.getQuaternionFromEuler (setEulerZYX + normalize)
 ORL_DI Q4 bullet_quat_from_euler(float roll, float pitch, float yaw) {
-  float sr, cr, sp, cp, sy, cy;
-  sincosf(0.5f * roll, &sr, &cr); sincosf(0.5f * pitch, &sp, &cp); sincosf(0.5f * yaw, &sy, &cy);
+  float sr, cr, sp, cp, sy, cy;       // half angles in [-pi/2, pi/2]: SFU sincos, abs. error < 4e-7
+  __sincosf(0.5f * roll, &sr, &cr); __sincosf(0.5f * pitch, &sp, &cp); __sincosf(0.5f * yaw, &sy, &cy);
   return qnormalize(q4(sr * cp * cy - cr * sp * sy, cr * sp * cy + sr * cp * sy, cr * cp * sy - sr * sp * cy,
                        cr * cp * cy + sr * sp * sy));
 }

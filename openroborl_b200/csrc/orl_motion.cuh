@@ -94,16 +94,20 @@ ORL_DI void motion_cycle_offset(const MotionTables& T, int clip, int cycle, floa
 }
 
 // Root part of MotionData.calc_frame (pos, rot after the cycle offset), motion_data.py:417-449
-ORL_DI void motion_root(const MotionTables& T, int clip, const BlendIdx& b, float3& pos, Q4& rot) {
+struct CycleOffset { float3 pos; float s, c; Q4 rot; };
+ORL_DI CycleOffset motion_cycle_offset(const MotionTables& T, int clip, int cycle) {
+  CycleOffset o;
+  motion_cycle_offset(T, clip, cycle, o.pos, o.s, o.c, o.rot);
+  return o;
+}
+ORL_DI void motion_root(const MotionTables& T, int clip, const BlendIdx& b, const CycleOffset& co, float3& pos, Q4& rot) {
   const float* a = T.frames + (size_t)(T.start[clip] + b.f0) * ORL_FRAME_STRIDE;
   const float* e = T.frames + (size_t)(T.start[clip] + b.f1) * ORL_FRAME_STRIDE;
   const float bl = (float)b.blend, ib = 1.0f - bl;
   pos = v3(ib * a[0] + bl * e[0], ib * a[1] + bl * e[1], ib * a[2] + bl * e[2]);
   rot = qstd(qslerp(q4(a[3], a[4], a[5], a[6]), q4(e[3], e[4], e[5], e[6]), bl));
-  float3 op; float s, c; Q4 orot;
-  motion_cycle_offset(T, clip, b.cycle, op, s, c, orot);
-  pos = qrot_z(s, c, pos) + op;
-  rot = qstd(qmul(orot, rot));
+  pos = qrot_z(co.s, co.c, pos) + co.pos;
+  rot = qstd(qmul(co.rot, rot));
 }
 ORL_DI float motion_joint(const MotionTables& T, int clip, const BlendIdx& b, int j) {
   const float a = T.frames[(size_t)(T.start[clip] + b.f0) * ORL_FRAME_STRIDE + 7 + j];
@@ -112,16 +116,14 @@ ORL_DI float motion_joint(const MotionTables& T, int clip, const BlendIdx& b, in
   return (1.0f - bl) * a + bl * e;
 }
 // MotionData.calc_frame_vel, motion_data.py:451-476
-ORL_DI void motion_root_vel(const MotionTables& T, int clip, const BlendIdx& b, float3& lin, float3& ang) {
+ORL_DI void motion_root_vel(const MotionTables& T, int clip, const BlendIdx& b, const CycleOffset& co, float3& lin, float3& ang) {
   const float* a = T.vels + (size_t)(T.start[clip] + b.f0) * ORL_FRAME_STRIDE;
   const float* e = T.vels + (size_t)(T.start[clip] + b.f1) * ORL_FRAME_STRIDE;
   const float bl = (float)b.blend, ib = 1.0f - bl;
   lin = v3(ib * a[0] + bl * e[0], ib * a[1] + bl * e[1], ib * a[2] + bl * e[2]);
   ang = v3(ib * a[3] + bl * e[3], ib * a[4] + bl * e[4], ib * a[5] + bl * e[5]);
-  float3 op; float s, c; Q4 orot;
-  motion_cycle_offset(T, clip, b.cycle, op, s, c, orot);
-  lin = qrot_z(s, c, lin);
-  ang = qrot_z(s, c, ang);
+  lin = qrot_z(co.s, co.c, lin);
+  ang = qrot_z(co.s, co.c, ang);
 }
 ORL_DI float motion_joint_vel(const MotionTables& T, int clip, const BlendIdx& b, int j) {
   const float a = T.vels[(size_t)(T.start[clip] + b.f0) * ORL_FRAME_STRIDE + 6 + j];
@@ -143,25 +145,31 @@ ORL_DI bool ref_in_warmup(const RefFrame& F, double time) { return F.warmup && t
 
 // One evaluation point on the reference clock: the FP64 index math is done once and shared by the
 // root / joint / velocity readers.
-struct RefSample { bool warm; BlendIdx b; };
+struct RefSample { bool warm; BlendIdx b; CycleOffset co; };
 ORL_DI RefSample ref_sample(const MotionTables& T, const RefFrame& F, double time) {
   RefSample s;
   s.warm = ref_in_warmup(F, time);
   s.b = motion_blend_idx(T, F.clip, time);
+  s.co = motion_cycle_offset(T, F.clip, s.b.cycle);
   return s;
 }
-// ImitationTask._calc_ref_pose root part (imitation_task.py:920-953)
-ORL_DI void ref_root(const MotionTables& T, const RefFrame& F, const RefSample& s, bool apply_origin, float3& pos, Q4& rot) {
+// root pose of the sample before the per-episode origin is applied
+ORL_DI void ref_root_raw(const MotionTables& T, const RefFrame& F, const RefSample& s, float3& pos, Q4& rot) {
   if (s.warm) {
     const float* w = T.warm_pose + (size_t)F.clip * ORL_FRAME_STRIDE;
     pos = v3(w[0], w[1], w[2]); rot = q4(w[3], w[4], w[5], w[6]);
   } else {
-    motion_root(T, F.clip, s.b, pos, rot);
+    motion_root(T, F.clip, s.b, s.co, pos, rot);
   }
-  if (apply_origin) {
-    rot = qmul(F.origin_rot, rot);
-    pos = qrot(F.origin_rot, pos) + F.origin_pos;
-  }
+}
+ORL_DI void ref_apply_origin(const RefFrame& F, float3& pos, Q4& rot) {
+  rot = qmul(F.origin_rot, rot);
+  pos = qrot(F.origin_rot, pos) + F.origin_pos;
+}
+// ImitationTask._calc_ref_pose root part (imitation_task.py:920-953)
+ORL_DI void ref_root(const MotionTables& T, const RefFrame& F, const RefSample& s, bool apply_origin, float3& pos, Q4& rot) {
+  ref_root_raw(T, F, s, pos, rot);
+  if (apply_origin) ref_apply_origin(F, pos, rot);
 }
 ORL_DI float ref_joint(const MotionTables& T, const RefFrame& F, const RefSample& s, int j) {
   if (s.warm) return T.warm_pose[(size_t)F.clip * ORL_FRAME_STRIDE + 7 + j];
@@ -170,7 +178,7 @@ ORL_DI float ref_joint(const MotionTables& T, const RefFrame& F, const RefSample
 // ImitationTask._calc_ref_vel (imitation_task.py:955-983, 1011-1018)
 ORL_DI void ref_root_vel(const MotionTables& T, const RefFrame& F, const RefSample& s, float3& lin, float3& ang) {
   if (s.warm) { lin = v3(0.f, 0.f, 0.f); ang = v3(0.f, 0.f, 0.f); }
-  else motion_root_vel(T, F.clip, s.b, lin, ang);
+  else motion_root_vel(T, F.clip, s.b, s.co, lin, ang);
   lin = qrot(F.origin_rot, lin);
   ang = qrot(F.origin_rot, ang);
 }
