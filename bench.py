@@ -201,6 +201,13 @@ def run_ours(args):
             pass
         hbm_peak, hbm_src = (peaks["hbm_gbs"], "MEASURED_PEAKS.json") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
         kern_s = np.median(step_ms) * 1e-3            # one launch = one control step of N robots
+        traffic = None                                # dram bytes per launch from the committed `ncu --set full` capture
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["orl_step_kernel"]
+            if int(tj["robots"]) == N:
+                traffic = int(tj["dram_bytes_read"]) + int(tj["dram_bytes_write"])
+        except Exception:
+            pass
         ach_tf = FLOP_PER_ROBOT_STEP * N / kern_s / 1e12
         ach_gb = BYTES_PER_ROBOT_STEP * N / kern_s / 1e9
         line = {
@@ -214,7 +221,7 @@ def run_ours(args):
                     "steps": Ke, "api": "orl_step_host (C ABI, page-locked host buffers)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp32", "achieved": ach_tf, "peak": tf.value, "unit": "TFLOP/s", "frac": ach_tf / tf.value if tf.value else None,
-                         "traffic": None, "kernel": "orl_step_kernel", "flop_per_robot_step": FLOP_PER_ROBOT_STEP,
+                         "traffic": traffic, "kernel": "orl_step_kernel", "flop_per_robot_step": FLOP_PER_ROBOT_STEP,
                          "peak_source": "FFMA micro-benchmark measured in this run (orl_fp32_peak)",
                          "hbm": {"achieved": ach_gb, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gb / hbm_peak, "peak_source": hbm_src,
                                  "bytes_per_robot_step": BYTES_PER_ROBOT_STEP}},
