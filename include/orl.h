@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define ORL_ABI_VERSION 1
+#define ORL_ABI_VERSION 2
 #define ORL_NUM_LEGS 4
 #define ORL_LEG_DOF 3
 #define ORL_NUM_MOTORS 12
@@ -79,6 +79,7 @@ typedef struct {
   float gravity_z;              /* -10 (quadruped_gym_env.py:200) */
   float contact_kn, contact_bn, contact_d0, contact_bt;
   float limit_k, limit_d, limit_e0;
+  float max_coordinate_velocity; /* clamp of every generalised velocity coordinate (btMultiBody default: 100) */
 } orl_config;
 
 /* One collision point: a sphere (radius may be 0) fixed to a body. */

@@ -6,7 +6,7 @@ There is deliberately no fallback: if `csrc/libopenroborl_b200.so` has not been 
 import ctypes as C
 import os
 
-ORL_ABI_VERSION = 1
+ORL_ABI_VERSION = 2
 NUM_LEGS, LEG_DOF, NUM_MOTORS = 4, 3, 12
 POSE_SIZE, VEL_SIZE, OBS_SIZE, NUM_TAR_FRAMES = 19, 18, 160, 4
 MAX_CP, MAX_LINKS, CYCLE_TABLE = 24, 32, 128
@@ -32,6 +32,7 @@ class OrlConfig(C.Structure):
         ("gravity_z", C.c_float),
         ("contact_kn", C.c_float), ("contact_bn", C.c_float), ("contact_d0", C.c_float), ("contact_bt", C.c_float),
         ("limit_k", C.c_float), ("limit_d", C.c_float), ("limit_e0", C.c_float),
+        ("max_coordinate_velocity", C.c_float),
     ]
 
 

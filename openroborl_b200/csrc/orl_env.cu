@@ -103,6 +103,7 @@ static void fill_dev_cfg(orl_env* e) {
   d.phys.dt = (float)c.sim_time_step; d.phys.g = -c.gravity_z;
   d.phys.kn = c.contact_kn; d.phys.bn = c.contact_bn; d.phys.inv_d0 = 1.0f / c.contact_d0; d.phys.bt = c.contact_bt;
   d.phys.klim = c.limit_k; d.phys.dlim = c.limit_d; d.phys.inv_e0 = 1.0f / c.limit_e0;
+  d.phys.vmax = c.max_coordinate_velocity;
 }
 
 static float f_from_i(int32_t i) { float f; memcpy(&f, &i, 4); return f; }
@@ -224,6 +225,7 @@ extern "C" int orl_create(const orl_config* cfg, const orl_robot_model* model, o
       if (model->leg[l].ee_body[i] < 0 || model->leg[l].ee_body[i] > 2) return fail(e, ORL_ERR_INVALID, "bad end-effector body");
   }
   if (!(cfg->contact_d0 > 0) || !(cfg->limit_e0 > 0)) return fail(e, ORL_ERR_INVALID, "contact_d0 and limit_e0 must be positive");
+  if (!(cfg->max_coordinate_velocity > 0)) return fail(e, ORL_ERR_INVALID, "max_coordinate_velocity must be positive");
   e->device = cfg->device;
   CUDA_TRY(e, cudaSetDevice(e->device));
   const size_t nstate = (size_t)cfg->num_robot * ORL_STRIDE;

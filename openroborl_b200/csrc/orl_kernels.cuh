@@ -293,8 +293,8 @@ ORL_DI void substep(const DevLeg& L, const DevModel& Mo, const PhysParams& P, co
   leg_dynamics<true, false, true>(L, Mo, P, Rb, D.pos.z, D.ang, D.lin, D.q, D.qd, tau, X, alpha, alin, qdd, nullptr);
   // semi-implicit Euler: velocities first, then positions with the new velocities
   const float3 lin_dot = cross_add(D.ang, D.lin, alin);
-  D.ang = fma3(P.dt, alpha, D.ang);
-  D.lin = fma3(P.dt, lin_dot, D.lin);
+  D.ang = clamp3(fma3(P.dt, alpha, D.ang), P.vmax);
+  D.lin = clamp3(fma3(P.dt, lin_dot, D.lin), P.vmax);
   D.pos = fma3(P.dt, D.lin, D.pos);
   {
     // quaternion exponential of w*dt: sin(h)/|w| and cos(h), h = |w| dt / 2 (Taylor series while h < 0.05)
@@ -312,7 +312,7 @@ ORL_DI void substep(const DevLeg& L, const DevModel& Mo, const PhysParams& P, co
   }
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
-    D.qd[k] = fmaf(P.dt, qdd[k], D.qd[k]);
+    D.qd[k] = fminf(fmaxf(fmaf(P.dt, qdd[k], D.qd[k]), -P.vmax), P.vmax);
     D.q[k] = fmaf(P.dt, D.qd[k], D.q[k]);
     D.r2[k] = D.r1[k]; D.r1[k] = qm_now[k];
   }
@@ -476,6 +476,12 @@ __global__ void __launch_bounds__(ORL_BLOCK_THREADS, ORL_STEP_MIN_BLOCKS) orl_st
     reward = C.w_pose * expf(-C.s_pose * pose_err) + C.w_vel * expf(-C.s_vel * vel_err) + C.w_ee * expf(-C.s_ee * ee_err) +
              C.w_root * expf(-C.s_root * root_err) + C.w_rootvel * expf(-C.s_rootvel * rootvel_err);
   }
+  // Guard (no reference counterpart): a non-finite state ends the episode with reward 0 instead of leaking NaN into
+  // observations and statistics.  Velocity clamping keeps the integrator finite; this only catches corrupted input.
+  const float chk = pos.x + pos.y + pos.z + quat.x + quat.y + quat.z + quat.w + q[0] + q[1] + q[2] + qd[0] + qd[1] + qd[2] +
+                    lin.x + lin.y + lin.z + ang.x + ang.y + ang.z;
+  const int broken = quad_or(!(fabsf(chk) < 3.0e38f) ? 1 : 0);
+  if (broken) reward = 0.f;
   __syncwarp();
   // 5. task.update (imitation_task.py:201-207, 734-761, 1020-1055)
   RefFrame F = load_ref_frame(S, C);
@@ -530,7 +536,7 @@ __global__ void __launch_bounds__(ORL_BLOCK_THREADS, ORL_STEP_MIN_BLOCKS) orl_st
     const float3 dp = nrp - pos;
     const float a = qangle_normalized(qmul(nrq, qconj(quat)));
     done = motion_is_over(E.mt, F.clip, time) || fall || (dot(dp, dp) > C.dist_thr2) || (fabsf(a) > C.rot_thr);
-    done |= (envstep1 >= C.max_episode_steps);
+    done |= (envstep1 >= C.max_episode_steps) || broken;
   }
   __syncwarp();
   // rollout statistics (SURVEY.md section 5 "metrics"): [sum reward, sum episode length, episodes, robot steps]

@@ -25,6 +25,7 @@ ORL_DI float dot(float3 a, float3 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, a.z 
 ORL_DI float3 cross(float3 a, float3 b) {
   return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
 }
+ORL_DI float3 clamp3(float3 v, float m) { return make_float3(fminf(fmaxf(v.x, -m), m), fminf(fmaxf(v.y, -m), m), fminf(fmaxf(v.z, -m), m)); }
 ORL_DI float3 fma3(float s, float3 a, float3 b) { return v3(fmaf(s, a.x, b.x), fmaf(s, a.y, b.y), fmaf(s, a.z, b.z)); }
 // c + a x b with every product fused
 ORL_DI float3 cross_add(float3 a, float3 b, float3 c) {

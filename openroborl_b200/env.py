@@ -22,7 +22,8 @@ TASK_DEFAULTS = dict(
     warmup_time=0.25, enable_cycle_sync=True, dist_fail_threshold=1.0, rot_fail_threshold=0.5 * math.pi)
 # physics model of this repo (DESIGN.md "physics model"); gravity from quadruped_gym_env.py:200
 PHYS_DEFAULTS = dict(gravity_z=-10.0, contact_kn=1.0e5, contact_bn=500.0, contact_d0=0.002, contact_bt=3000.0,
-                     limit_k=1000.0, limit_d=2.0, limit_e0=0.01, mu_plane=1.0, margin_factor=0.02)
+                     limit_k=1000.0, limit_d=2.0, limit_e0=0.01, mu_plane=1.0, margin_factor=0.02,
+                     max_coordinate_velocity=100.0)
 
 _INT_FIELDS = ("clip", "warmup", "substep_counter", "step_counter", "env_step_counter", "episode")
 _F64_FIELDS = ("time_offset", "prev_phase")
@@ -78,7 +79,8 @@ class BatchedImitationEnv(object):
                   "pose_err_scale", "velocity_err_scale", "end_effector_err_scale", "end_effector_height_err_scale",
                   "root_pose_err_scale", "root_velocity_err_scale", "dist_fail_threshold", "rot_fail_threshold"):
             setattr(cfg, k, float(self.task[k]))
-        for k in ("gravity_z", "contact_kn", "contact_bn", "contact_d0", "contact_bt", "limit_k", "limit_d", "limit_e0"):
+        for k in ("gravity_z", "contact_kn", "contact_bn", "contact_d0", "contact_bt", "limit_k", "limit_d", "limit_e0",
+                  "max_coordinate_velocity"):
             setattr(cfg, k, float(self.phys[k]))
         self.cfg = cfg
         self.env_time_step = cfg.env_time_step

@@ -19,7 +19,7 @@ from .robots import get_spec, classify_links
 DEFAULT_PHYS = dict(
     gravity=(0.0, 0.0, -10.0),   # quadruped_gym_env.py:200
     kn=1.0e5, bn=500.0, d0=0.002, bt=3000.0, mu_plane=1.0,
-    k_lim=1000.0, d_lim=2.0, e0=0.01, margin_factor=0.02)
+    k_lim=1000.0, d_lim=2.0, e0=0.01, margin_factor=0.02, max_coordinate_velocity=100.0)
 
 # imitation_task.py:45-58 as configured by run.py:58-64
 DEFAULT_TASK = dict(
@@ -371,9 +371,14 @@ class OracleEnv(object):
 
     def integrate(self, nudot):
         dt = self.spec.time_step
-        self.ang = self.ang + dt * nudot[:, 0:3]
-        self.lin = self.lin + dt * nudot[:, 3:6]
-        self.qd = self.qd + dt * nudot[:, 6:]
+        # every generalised velocity coordinate is clamped like btMultiBody::applyDeltaVeeMultiDof
+        # (m_maxCoordinateVelocity = 100; Bullet3 knowledge, not in /root/reference): keeps the state finite when
+        # the reference's own velocity tables spike (quaternion sign flips in laikago_spin / hopturn / turn give
+        # |w| up to 375 rad/s at reference-state initialisation)
+        vmax = self.phys["max_coordinate_velocity"]
+        self.ang = np.clip(self.ang + dt * nudot[:, 0:3], -vmax, vmax)
+        self.lin = np.clip(self.lin + dt * nudot[:, 3:6], -vmax, vmax)
+        self.qd = np.clip(self.qd + dt * nudot[:, 6:], -vmax, vmax)
         self.pos = self.pos + dt * self.lin
         wn = np.sqrt(np.sum(self.ang ** 2, axis=-1))
         half = 0.5 * wn * dt

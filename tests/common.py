@@ -58,7 +58,8 @@ def oracle_phys_from_product(phys):
     """Map the product's physics parameter names to the oracle's."""
     return dict(gravity=(0.0, 0.0, phys["gravity_z"]), kn=phys["contact_kn"], bn=phys["contact_bn"], d0=phys["contact_d0"],
                 bt=phys["contact_bt"], mu_plane=phys["mu_plane"], k_lim=phys["limit_k"], d_lim=phys["limit_d"],
-                e0=phys["limit_e0"], margin_factor=phys["margin_factor"])
+                e0=phys["limit_e0"], margin_factor=phys["margin_factor"],
+                max_coordinate_velocity=phys["max_coordinate_velocity"])
 
 
 def sync_oracle_from_product(oracle, st):

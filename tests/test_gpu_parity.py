@@ -190,6 +190,64 @@ def test_control_step_matches_oracle(which, request):
     print("worst errors over 4 steps:", worst)
 
 
+def test_velocity_clamp_matches_oracle_and_state_stays_finite(laikago):
+    """The reference's own velocity tables spike (laikago_spin: |w| = 375 rad/s where the clip's quaternions flip
+    sign), so reference-state initialisation can start a robot with such a velocity.  Every generalised velocity
+    coordinate is clamped to +-100 (btMultiBody) in the oracle and in the kernel."""
+    env, orc = laikago
+    env.reset(); orc.reset()
+    st = env.get_state()
+    N = env.num_robot
+    st["ang"] = np.tile(np.array([-83.8, -167.7, -255.4], np.float32), (N, 1))
+    st["qd"] = np.full((N, 12), 150.0, np.float32) * np.sign(np.random.default_rng(0).normal(size=(N, 12))).astype(np.float32)
+    env.set_state(st)
+    common.sync_oracle_from_product(orc, env.get_state())
+    act = np.zeros((N, 12), np.float32)
+    o, r, d = env.step(torch.as_tensor(act, device=env.device))
+    orc.step(act.astype(np.float64))
+    s2 = env.get_state()
+    for k in ("pos", "quat", "q", "lin", "ang", "qd"):
+        assert np.isfinite(s2[k]).all(), k
+    for k in ("lin", "ang", "qd"):
+        assert np.abs(s2[k]).max() <= 100.0 + 1e-3 and np.abs(getattr(orc, k)).max() <= 100.0 + 1e-9
+    assert np.isfinite(o.cpu().numpy()).all() and np.isfinite(r.cpu().numpy()).all()
+    # violent, chaotic motion: FP32 and FP64 trajectories only agree in the bulk
+    assert np.median(np.abs(s2["ang"] - orc.ang)) < 1.0 and np.median(np.abs(s2["pos"] - orc.pos)) < 1e-2
+
+
+def test_motion_library_with_velocity_spikes_stays_finite():
+    clips = ["laikago_pace", "laikago_trot", "laikago_spin", "laikago_hopturn", "laikago_sidesteps"]
+    N = 4096
+    env = common.make_product("laikago", clips, N, seed=0, auto_reset=True)
+    env.reset()
+    assert np.abs(env.motion_tables()["vels"][:, 3:6]).max() > 300.0       # the spike is in the reference's data
+    gen = torch.Generator(device=env.device); gen.manual_seed(0)
+    acts = [torch.randn((N, 12), device=env.device, generator=gen) * 0.125 for _ in range(4)]
+    finite = torch.ones((), dtype=torch.bool, device=env.device)
+    for i in range(150):
+        o, r, d = env.step(acts[i % 4])
+        finite &= torch.isfinite(o).all() & torch.isfinite(r).all()
+    assert bool(finite)
+    st = env.stats()
+    assert np.isfinite(st).all() and st[2] > 0
+    s = env.get_state()
+    assert np.isfinite(s["pos"]).all() and np.isfinite(s["qd"]).all()
+    env.close()
+
+
+def test_non_finite_state_ends_the_episode():
+    N = 16
+    env = common.make_product("laikago", ["laikago_pace"], N, seed=1)
+    env.reset()
+    st = env.get_state()
+    st["pos"][3, 2] = np.nan
+    env.set_state(st)
+    o, r, d = env.step(torch.zeros((N, 12), device=env.device))
+    d, r = d.cpu().numpy(), r.cpu().numpy()
+    assert d[3] == 1 and r[3] == 0.0 and d.sum() == 1 and np.isfinite(r).all()
+    env.close()
+
+
 def test_time_limit_and_termination_thresholds(laikago):
     env, orc = laikago
     env.reset(); orc.reset()
