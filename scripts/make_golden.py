@@ -15,6 +15,8 @@ The GPU box has no /root/reference, so everything the tests and bench need from 
                          (motion_data.py, pose3d.py, action_filter.py, minitaur_motor.py) imported from the
                          reference tree with a numpy shim for the absent third-party
                          `pybullet_utils.transformations` (oracle/xform.py restates its algorithms).
+* ref_randomizer_kat.npz: sampled parameters and robot-setter arguments of the reference's own
+                         ControllableEnvRandomizerFromConfig (seeded RandomState, recording robot stub).
 * ref_task_trace.npz   : per-step traces (observation, reward, done, task internals) produced by the
                          reference's own ImitationTask / Minitaur / LocomotionGymEnv / WrapperEnv classes running
                          against a fake BulletClient (scripts/fake_bullet.py) whose physics backend is oracle/rbd.py.
@@ -157,6 +159,52 @@ def motion_kat(ref):
     print("ref_motion_kat.npz:", len(out), "arrays")
 
 
+def randomizer_kat(ref):
+    """Known answers from the reference's own ControllableEnvRandomizerFromConfig driven with a recording robot."""
+    sys.path.insert(0, os.path.join(ref, "OpenRoboRL"))
+    tf = types.ModuleType("tensorflow")
+    tf.logging = types.SimpleNamespace(info=lambda *a, **k: None)
+    sys.modules.setdefault("tensorflow", tf)
+    from envs.utilities.randomizer import controllable_env_randomizer_from_config as crc
+
+    class Robot(object):
+        num_motors = 12
+
+        def __init__(self):
+            rng = np.random.RandomState(7)
+            self.base_mass = list(rng.uniform(1, 14, size=5))          # chassis link ids: base + 4 hip links
+            self.leg_mass = list(rng.uniform(0.05, 2, size=12))        # 8 leg links + 4 motor links
+            self.base_inertia = [tuple(rng.uniform(1e-3, 0.3, size=3)) for _ in range(5)]
+            self.leg_inertia = [tuple(rng.uniform(1e-5, 1e-2, size=3)) for _ in range(12)]
+            self.calls = {}
+
+        def get_base_mass_from_urdf(self): return self.base_mass
+        def get_leg_mass_from_urdf(self): return self.leg_mass
+        def get_base_inertia_from_urdf(self): return self.base_inertia
+        def get_leg_inertia_from_urdf(self): return self.leg_inertia
+        def get_num_knee_joints(self): return 8
+
+        def __getattr__(self, name):
+            if name.startswith("set_"):
+                return lambda v, _n=name: self.calls.__setitem__(_n, np.array(v, dtype=np.float64))
+            raise AttributeError(name)
+
+    out = {}
+    for seed in (0, 1, 12345):
+        robot = Robot()
+        r = crc.ControllableEnvRandomizerFromConfig(verbose=False, randomization_seed=seed)
+        r.randomize_env(robot)
+        out["seed%d/uniforms" % seed] = np.random.RandomState(seed).random_sample(28)
+        for k, v in r.get_randomization_parameters().items():
+            out["seed%d/param/%s" % (seed, k)] = np.atleast_1d(np.asarray(v, dtype=np.float64))
+        for k, v in robot.calls.items():
+            out["seed%d/call/%s" % (seed, k)] = v
+        out["robot/base_mass"] = np.array(robot.base_mass); out["robot/leg_mass"] = np.array(robot.leg_mass)
+        out["robot/base_inertia"] = np.array(robot.base_inertia); out["robot/leg_inertia"] = np.array(robot.leg_inertia)
+    np.savez_compressed(os.path.join(GOLD, "ref_randomizer_kat.npz"), **out)
+    print("ref_randomizer_kat.npz:", len(out), "arrays;", sorted(k for k in out if k.startswith("seed0/")))
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--reference", default="/root/reference")
@@ -167,6 +215,7 @@ if __name__ == "__main__":
     motion_clips(args.reference)
     policies(args.reference)
     motion_kat(args.reference)
+    randomizer_kat(args.reference)
     if not args.skip_trace:
         try:
             from scripts import make_trace
