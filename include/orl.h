@@ -80,7 +80,19 @@ typedef struct {
   float contact_kn, contact_bn, contact_d0, contact_bt;
   float limit_k, limit_d, limit_e0;
   float max_coordinate_velocity; /* clamp of every generalised velocity coordinate (btMultiBody default: 100) */
+  /* Domain randomizer.  Replaces ControllableEnvRandomizerFromConfig.randomize_env
+   * (R/envs/utilities/randomizer/controllable_env_randomizer_from_config.py:92-122), run by Minitaur.reset when
+   * enable_randomizer is set (minitaur.py:273-276).  Ranges in the reference's SORTED parameter order
+   * (ORL_RAND_*; defaults minitaur_env_randomizer_config.py:22-36). */
+  int32_t enable_randomizer;
+  float rand_lo[8], rand_hi[8];
+  float joint_friction_k;       /* slope of the regularised Coulomb joint friction, N m s / rad (this repo's model) */
+  float mu_plane;               /* lateral friction of the ground plane (combined with the randomised foot friction) */
 } orl_config;
+
+enum { ORL_RAND_BATTERY = 0, ORL_RAND_INERTIA = 1, ORL_RAND_JOINT_FRICTION = 2, ORL_RAND_LATENCY = 3,
+       ORL_RAND_LATERAL_FRICTION = 4, ORL_RAND_MASS = 5, ORL_RAND_MOTOR_FRICTION = 6, ORL_RAND_MOTOR_STRENGTH = 7 };
+#define ORL_RAND_DRAWS 28       /* 1 + 2 + 8 + 1 + 1 + 2 + 1 + 12 uniforms per reset, in that order */
 
 /* One collision point: a sphere (radius may be 0) fixed to a body. */
 typedef struct {
@@ -100,6 +112,10 @@ typedef struct {
   float mass[ORL_LEG_DOF];
   float com[ORL_LEG_DOF][3];
   float inertia[ORL_LEG_DOF][6];/* about the COM, body frame: xx xy xz yy yz zz */
+  float inertia_par[ORL_LEG_DOF][6]; /* the parallel-axis share of `inertia` (merged fixed children): it scales with the
+                                   randomised MASS ratio, the rest with the INERTIA ratio (minitaur.py:935-1039) */
+  int32_t rand_class[ORL_LEG_DOF];   /* 0: links of the chassis set (base ratios), 1: leg/motor set (leg ratios), -1: mixed */
+  int32_t friction_draw[ORL_LEG_DOF];/* index of this joint's sample in set_joint_friction (minitaur.py:1063-1070) or -1 */
   float lower[ORL_LEG_DOF], upper[ORL_LEG_DOF], damping[ORL_LEG_DOF];
   /* motor model (laikago.py:50-66, mini_cheetah.py:51-67, minitaur_motor.py:104-173) */
   float dir[ORL_LEG_DOF], offset[ORL_LEG_DOF], kp[ORL_LEG_DOF], kd[ORL_LEG_DOF], init_angle[ORL_LEG_DOF];
@@ -139,6 +155,7 @@ typedef struct {
   int32_t ep_return;
   int32_t obs_quat;
   int32_t motor_strength;
+  int32_t rand_params;          /* 12: base/leg mass ratio, base/leg inertia ratio, latency, foot friction x plane (-1: model), knee friction[4], pad */
 } orl_state_layout;
 
 /* ---- lifetime -------------------------------------------------------------------------------- */
@@ -200,6 +217,9 @@ int orl_motion_lookup(orl_env* env, const int32_t* clip_dev, const double* time_
 int orl_fk(orl_env* env, const float* pose_dev, int32_t n, float* com_dev, void* stream);
 /* Joint-space inertia matrix (CRBA), generalised-velocity order [root lin(3), root ang(3), joints(12)]:
  * pose_dev [n][19] -> M_dev [n][18][18].  Oracle: pybullet.calculateMassMatrix (north_star). */
+/* Randomizer values [n][12] (layout of orl_state_layout.rand_params) used by the three dynamics entry points below;
+ * NULL (default) = the model's own masses, inertias and friction. */
+int orl_set_dynamics_rand(orl_env* env, const float* rand_dev);
 int orl_mass_matrix(orl_env* env, const float* pose_dev, int32_t n, float* M_dev, void* stream);
 /* Inverse dynamics (RNEA), no contact: pose [n][19], vel [n][18], acc [n][18] (classical time derivative
  * of vel) -> generalised forces tau [n][18].  Oracle: pybullet.calculateInverseDynamics (north_star). */

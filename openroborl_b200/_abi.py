@@ -33,6 +33,8 @@ class OrlConfig(C.Structure):
         ("contact_kn", C.c_float), ("contact_bn", C.c_float), ("contact_d0", C.c_float), ("contact_bt", C.c_float),
         ("limit_k", C.c_float), ("limit_d", C.c_float), ("limit_e0", C.c_float),
         ("max_coordinate_velocity", C.c_float),
+        ("enable_randomizer", C.c_int32), ("rand_lo", C.c_float * 8), ("rand_hi", C.c_float * 8),
+        ("joint_friction_k", C.c_float), ("mu_plane", C.c_float),
     ]
 
 
@@ -45,6 +47,7 @@ class OrlLegModel(C.Structure):
     _fields_ = [
         ("R_fix", (C.c_float * 9) * LEG_DOF), ("p_fix", (C.c_float * 3) * LEG_DOF),
         ("mass", C.c_float * LEG_DOF), ("com", (C.c_float * 3) * LEG_DOF), ("inertia", (C.c_float * 6) * LEG_DOF),
+        ("inertia_par", (C.c_float * 6) * LEG_DOF), ("rand_class", C.c_int32 * LEG_DOF), ("friction_draw", C.c_int32 * LEG_DOF),
         ("lower", C.c_float * LEG_DOF), ("upper", C.c_float * LEG_DOF), ("damping", C.c_float * LEG_DOF),
         ("dir", C.c_float * LEG_DOF), ("offset", C.c_float * LEG_DOF), ("kp", C.c_float * LEG_DOF),
         ("kd", C.c_float * LEG_DOF), ("init_angle", C.c_float * LEG_DOF),
@@ -69,7 +72,7 @@ class OrlStateLayout(C.Structure):
         "stride", "pos", "quat", "q", "lin", "ang", "qd", "filt_x", "filt_y", "prev_filtered", "ring1", "ring2",
         "imu_hist", "act_hist", "ang_hist", "ref_pose", "ref_vel", "origin_pos", "origin_rot", "time_offset",
         "prev_phase", "clip", "warmup", "substep_counter", "step_counter", "env_step_counter", "episode",
-        "ep_return", "obs_quat", "motor_strength")]
+        "ep_return", "obs_quat", "motor_strength", "rand_params")]
 
 
 # every symbol include/orl.h declares: name -> (restype, argtypes)
@@ -94,6 +97,7 @@ SYMBOLS = {
     "orl_stats": (C.c_int, [_P, _P, C.c_int32]),
     "orl_motion_lookup": (C.c_int, [_P, _P, _P, C.c_int32, _P, _P, _P, _P, _P, _P, _P]),
     "orl_fk": (C.c_int, [_P, _P, C.c_int32, _P, _P]),
+    "orl_set_dynamics_rand": (C.c_int, [_P, _P]),
     "orl_mass_matrix": (C.c_int, [_P, _P, C.c_int32, _P, _P]),
     "orl_inverse_dynamics": (C.c_int, [_P, _P, _P, _P, C.c_int32, _P, _P]),
     "orl_forward_dynamics": (C.c_int, [_P, _P, _P, _P, C.c_int32, _P, _P]),

@@ -18,6 +18,8 @@ struct __align__(16) DevJoint {
   float4 c1;           // com.y com.z lower upper
   float4 m0;           // damping dir offset kp
   float4 m1;           // kd init_angle motor(int bits) bounding radius of this body's collision points
+  float4 i2;           // parallel-axis share of the inertia: xx xy xz yy   (scales with the randomised mass ratio)
+  float4 i3;           // ... yz zz, randomizer class (int bits: 0 chassis set, 1 leg set), friction draw index (int bits, -1: none)
 };
 struct __align__(16) DevCp {
   float4 a;            // local xyz, radius

@@ -35,6 +35,7 @@ struct orl_env {
   float* d_act; float* d_obs; float* d_rew; uint8_t* d_done; uint8_t* d_mask;
   cudaStream_t stream;
   cudaEvent_t ev_chunk[ORL_D2H_CHUNKS];
+  const float* parity_rand;        // orl_set_dynamics_rand
 };
 
 static int fail(orl_env* e, int code, const char* fmt, ...) {
@@ -104,6 +105,10 @@ static void fill_dev_cfg(orl_env* e) {
   d.phys.kn = c.contact_kn; d.phys.bn = c.contact_bn; d.phys.inv_d0 = 1.0f / c.contact_d0; d.phys.bt = c.contact_bt;
   d.phys.klim = c.limit_k; d.phys.dlim = c.limit_d; d.phys.inv_e0 = 1.0f / c.limit_e0;
   d.phys.vmax = c.max_coordinate_velocity;
+  d.phys.kfric = c.joint_friction_k;
+  d.randomize = c.enable_randomizer;
+  d.mu_plane = c.mu_plane;
+  for (int i = 0; i < 8; ++i) { d.rand_lo[i] = c.rand_lo[i]; d.rand_hi[i] = c.rand_hi[i]; }
 }
 
 static float f_from_i(int32_t i) { float f; memcpy(&f, &i, 4); return f; }
@@ -179,6 +184,8 @@ static void pack_model(const orl_robot_model& m, DevModel& d) {
       J.c1 = make_float4(L.com[k][1], L.com[k][2], L.lower[k], L.upper[k]);
       J.m0 = make_float4(L.damping[k], L.dir[k], L.offset[k], L.kp[k]);
       J.m1 = make_float4(L.kd[k], L.init_angle[k], f_from_i(L.motor[k]), brad[k]);
+      J.i2 = make_float4(L.inertia_par[k][0], L.inertia_par[k][1], L.inertia_par[k][2], L.inertia_par[k][3]);
+      J.i3 = make_float4(L.inertia_par[k][4], L.inertia_par[k][5], f_from_i(L.rand_class[k]), f_from_i(L.friction_draw[k]));
     }
     for (int e = 0; e < 2; ++e)
       D.ee[e] = make_float4(L.ee_local[e][0], L.ee_local[e][1], L.ee_local[e][2], f_from_i(L.ee_body[e]));
@@ -226,6 +233,16 @@ extern "C" int orl_create(const orl_config* cfg, const orl_robot_model* model, o
   }
   if (!(cfg->contact_d0 > 0) || !(cfg->limit_e0 > 0)) return fail(e, ORL_ERR_INVALID, "contact_d0 and limit_e0 must be positive");
   if (!(cfg->max_coordinate_velocity > 0)) return fail(e, ORL_ERR_INVALID, "max_coordinate_velocity must be positive");
+  if (cfg->enable_randomizer) {
+    for (int i = 0; i < 8; ++i)
+      if (!(cfg->rand_hi[i] >= cfg->rand_lo[i])) return fail(e, ORL_ERR_INVALID, "randomizer range %d is empty", i);
+    if (!(cfg->rand_lo[ORL_RAND_MASS] > 0) || !(cfg->rand_lo[ORL_RAND_INERTIA] > 0)) return fail(e, ORL_ERR_INVALID, "mass / inertia ratios must be positive");
+    for (int l = 0; l < ORL_NUM_LEGS; ++l)
+      for (int k = 0; k < 3; ++k) {
+        if (model->leg[l].rand_class[k] < 0) return fail(e, ORL_ERR_INVALID, "leg %d body %d merges links of the chassis and the leg set: randomizer unsupported", l, k);
+        if (model->leg[l].friction_draw[k] >= 8) return fail(e, ORL_ERR_INVALID, "bad friction_draw");
+      }
+  }
   e->device = cfg->device;
   CUDA_TRY(e, cudaSetDevice(e->device));
   const size_t nstate = (size_t)cfg->num_robot * ORL_STRIDE;
@@ -247,6 +264,7 @@ extern "C" int orl_create(const orl_config* cfg, const orl_robot_model* model, o
       float* S = init.data() + (size_t)r * ORL_STRIDE;
       for (int m = 0; m < 12; ++m) S[S_STRENGTH + m] = 1.f;
       S[S_OBSQ + 3] = 1.f; S[S_OROT + 3] = 1.f; S[S_QUAT + 3] = 1.f;
+      S[S_RAND + 0] = S[S_RAND + 1] = S[S_RAND + 2] = S[S_RAND + 3] = 1.f; S[S_RAND + 5] = -1.f;
     }
     CUDA_TRY(e, cudaMemcpy(e->d_state, init.data(), nstate * sizeof(float), cudaMemcpyHostToDevice));
   }
@@ -569,6 +587,7 @@ extern "C" int orl_state_layout_get(const orl_env* e, orl_state_layout* o) {
   o->clip = S_CLIP; o->warmup = S_WARM; o->substep_counter = S_SUBSTEP; o->step_counter = S_STEP;
   o->env_step_counter = S_ENVSTEP; o->episode = S_EPISODE; o->ep_return = S_EPRET; o->obs_quat = S_OBSQ;
   o->motor_strength = S_STRENGTH;
+  o->rand_params = S_RAND;
   return ORL_OK;
 }
 
@@ -632,8 +651,13 @@ static int dyn_call(orl_env* e, int mode, const float* pose, const float* vel, c
   if (!e) return ORL_ERR_INVALID;
   if (n <= 0) return ORL_OK;
   if (mode == 0) CUDA_TRY(e, cudaMemsetAsync(out, 0, (size_t)n * 324 * sizeof(float), (cudaStream_t)stream));
-  orl_dyn_kernel<<<(n * 4 + ORL_DYN_BLOCK - 1) / ORL_DYN_BLOCK, ORL_DYN_BLOCK, 0, (cudaStream_t)stream>>>(e->d_model, e->dev.cfg.phys, mode, pose, vel, in, n, out);
+  orl_dyn_kernel<<<(n * 4 + ORL_DYN_BLOCK - 1) / ORL_DYN_BLOCK, ORL_DYN_BLOCK, 0, (cudaStream_t)stream>>>(e->d_model, e->dev.cfg.phys, mode, pose, vel, in, e->parity_rand, n, out);
   return check_launch(e, "orl_dyn_kernel");
+}
+extern "C" int orl_set_dynamics_rand(orl_env* e, const float* rand_dev) {
+  if (!e) return ORL_ERR_INVALID;
+  e->parity_rand = rand_dev;
+  return ORL_OK;
 }
 extern "C" int orl_mass_matrix(orl_env* e, const float* pose_dev, int32_t n, float* M_dev, void* stream) {
   return dyn_call(e, 0, pose_dev, nullptr, nullptr, n, M_dev, stream);

@@ -25,6 +25,9 @@ struct DevCfg {
   float dist_thr2, rot_thr;
   float fb0, fb1, fb2, fa1, fa2;   // Butterworth (action_filter.py:129-217)
   PhysParams phys;
+  int randomize;                   // domain randomizer on reset (minitaur.py:273-276)
+  float mu_plane;
+  float rand_lo[8], rand_hi[8];    // ranges in the reference's sorted parameter order (ORL_RAND_*)
 };
 
 struct DevEnv {
@@ -214,6 +217,36 @@ ORL_DI void reset_robot(float* S, const DevEnv& E, const DevModel& Mo, int gid, 
     st_f64(S + S_TOFF, toff);
     stq(S + S_OBSQ, q4(0.f, 0.f, 0.f, 1.f));
   }
+  // domain randomizer (Minitaur.reset -> randomize_env, minitaur.py:273-276): ORL_RAND_DRAWS uniforms of this
+  // (robot, episode), consumed in the reference's sorted parameter order; u = (word + 0.5) / 2^32
+  if (C.randomize) {
+    double val[ORL_RAND_DRAWS];
+    const int first[9] = {0, 1, 3, 11, 12, 13, 15, 16, 28};
+#pragma unroll 1
+    for (int b = 0; b < ORL_RAND_DRAWS / 4; ++b) {
+      uint32_t w[4];
+      philox4x32((uint32_t)gid, (uint32_t)episode, 2u + (uint32_t)b, 0u, (uint32_t)(C.seed & 0xffffffffull), (uint32_t)(C.seed >> 32), w);
+      for (int j = 0; j < 4; ++j) val[4 * b + j] = ((double)w[j] + 0.5) * (1.0 / 4294967296.0);
+    }
+#pragma unroll 1
+    for (int p = 0; p < 8; ++p)
+      for (int i = first[p]; i < first[p + 1]; ++i) {
+        const double smp = -1.0 + 2.0 * val[i];                                         // np.random.uniform(-1, 1)
+        val[i] = (smp - (-1.0)) / 2.0 * ((double)C.rand_hi[p] - (double)C.rand_lo[p]) + (double)C.rand_lo[p];
+      }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) S[S_STRENGTH + __float_as_int(L.j[k].m1.z)] = (float)val[16 + __float_as_int(L.j[k].m1.z)];
+    float fr = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { const int d = __float_as_int(L.j[k].i3.w); if (d >= 0) fr = (float)val[3 + d]; }
+    S[S_RAND + 6 + leg] = fr;
+    if (leg == 0) {
+      S[S_RAND + 0] = (float)val[13]; S[S_RAND + 1] = (float)val[14];                  // mass: base, legs
+      S[S_RAND + 2] = (float)val[1]; S[S_RAND + 3] = (float)val[2];                    // inertia: base, legs
+      S[S_RAND + 4] = (float)val[11];                                                  // latency
+      S[S_RAND + 5] = (float)val[12] * C.mu_plane;                                     // lateral friction of the foot links
+    }
+  }
   // _reset_ref_motion
   RefFrame F;
   F.clip = clip; F.warmup = warm; F.warmup_time = C.warmup_time;
@@ -263,6 +296,8 @@ struct LaneDyn {
 struct LaneCtl {
   float target[3], prevf[3];
   float strength[3];
+  float fric[3];             // Coulomb friction torque of this lane's joints (randomizer; 0: none)
+  RandLane rl;
   float mac, inv_ar;
   int capture;
   bool first_step;
@@ -287,10 +322,11 @@ ORL_DI void substep(const DevLeg& L, const DevModel& Mo, const PhysParams& P, co
     const float tm = strength * (-1.0f * (m0.w * (qm - cmd)) - m1.x * qdm);   // minitaur_motor.py:163-166
     const float e = fmaxf(0.f, c1.z - D.q[k]) - fmaxf(0.f, D.q[k] - c1.w);
     tau[k] = fmaf(tm, m0.y, fmaf(P.klim, e, -(fmaf(P.dlim, fminf(1.0f, fabsf(e) * P.inv_e0), m0.x)) * D.qd[k]));
+    tau[k] -= fminf(fmaxf(P.kfric * D.qd[k], -Ctl.fric[k]), Ctl.fric[k]);     // set_joint_friction (minitaur.py:1063-1070), regularised
     qm_now[k] = qm;
   }
   float3 alpha, alin; float qdd[3];
-  leg_dynamics<true, false, true>(L, Mo, P, Rb, D.pos.z, D.ang, D.lin, D.q, D.qd, tau, X, alpha, alin, qdd, nullptr);
+  leg_dynamics<true, false, true>(L, Mo, P, Rb, D.pos.z, D.ang, D.lin, D.q, D.qd, tau, X, Ctl.rl, alpha, alin, qdd, nullptr);
   // semi-implicit Euler: velocities first, then positions with the new velocities
   const float3 lin_dot = cross_add(D.ang, D.lin, alin);
   D.ang = clamp3(fma3(P.dt, alpha, D.ang), P.vmax);
@@ -377,7 +413,15 @@ __global__ void __launch_bounds__(ORL_BLOCK_THREADS, ORL_STEP_MIN_BLOCKS) orl_st
   for (int k = 0; k < 3; ++k) { D.q[k] = q[k]; D.qd[k] = qd[k]; D.r1[k] = r1[k]; D.r2[k] = r2[k]; }
   LaneCtl Ctl;
 #pragma unroll
-  for (int k = 0; k < 3; ++k) { Ctl.target[k] = target[k]; Ctl.prevf[k] = prevf[k]; Ctl.strength[k] = S[S_STRENGTH + __float_as_int(L.j[k].m1.z)]; }
+  for (int k = 0; k < 3; ++k) {
+    Ctl.target[k] = target[k]; Ctl.prevf[k] = prevf[k]; Ctl.strength[k] = S[S_STRENGTH + __float_as_int(L.j[k].m1.z)];
+    Ctl.fric[k] = __float_as_int(L.j[k].i3.w) >= 0 ? S[S_RAND + 6 + leg] : 0.f;
+  }
+  Ctl.rl.base_mass_ratio = S[S_RAND + 0]; Ctl.rl.base_inertia_ratio = S[S_RAND + 2]; Ctl.rl.mu_foot = S[S_RAND + 5];
+  {
+    const float ratios[4] = {S[S_RAND + 0], S[S_RAND + 1], S[S_RAND + 2], S[S_RAND + 3]};
+    fill_scaled_inertia(L, ratios, X + ORL_XI_BASE * ORL_X_STRIDE);
+  }
   Ctl.first_step = first_step; Ctl.mac = Mo->b1.w;
   const int AR = C.action_repeat;
   Ctl.inv_ar = 1.0f / (float)AR; Ctl.capture = AR - 3;
@@ -632,7 +676,7 @@ __global__ void orl_fk_kernel(const DevModel* Mo, const float* pose, int n, floa
 // mode 0: mass matrix [n][18][18]; 1: inverse dynamics tau [n][18]; 2: forward dynamics acc [n][18]
 // generalised velocity order of the interface: [lin(3), ang(3), joints(12)]
 __global__ void orl_dyn_kernel(const DevModel* Mo, PhysParams P, int mode, const float* pose, const float* vel,
-                               const float* in, int n, float* out) {
+                               const float* in, const float* rand /* [n][12] randomizer values (S_RAND layout) or null */, int n, float* out) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int i = min(t >> 2, n - 1), leg = t & 3;
   const bool valid = (t >> 2) < n;
@@ -652,8 +696,14 @@ __global__ void orl_dyn_kernel(const DevModel* Mo, PhysParams P, int mode, const
   DynExport ex;
   __shared__ float4 Xs[ORL_DYN_BLOCK / 32 * ORL_X_FLOAT4_PER_LANE * ORL_X_STRIDE];     // per-lane dynamics scratch
   float4* X = Xs + (threadIdx.x >> 5) * (ORL_X_FLOAT4_PER_LANE * ORL_X_STRIDE) + (threadIdx.x & 31);
-  if (mode == 2) leg_dynamics<true, false, false>(L, *Mo, P, Rb, p[2], ang, lin, q, qd, tau, X, alpha, alin, qdd, nullptr);
-  else leg_dynamics<false, true, false>(L, *Mo, P, Rb, p[2], ang, lin, q, qd, tau, X, alpha, alin, qdd, &ex);
+  RandLane RL; RL.base_mass_ratio = rand ? rand[(size_t)i * 12 + 0] : 1.f; RL.base_inertia_ratio = rand ? rand[(size_t)i * 12 + 2] : 1.f;
+  RL.mu_foot = rand ? rand[(size_t)i * 12 + 5] : -1.f;
+  {
+    const float ratios[4] = {RL.base_mass_ratio, rand ? rand[(size_t)i * 12 + 1] : 1.f, RL.base_inertia_ratio, rand ? rand[(size_t)i * 12 + 3] : 1.f};
+    fill_scaled_inertia(L, ratios, X + ORL_XI_BASE * ORL_X_STRIDE);
+  }
+  if (mode == 2) leg_dynamics<true, false, false>(L, *Mo, P, Rb, p[2], ang, lin, q, qd, tau, X, RL, alpha, alin, qdd, nullptr);
+  else leg_dynamics<false, true, false>(L, *Mo, P, Rb, p[2], ang, lin, q, qd, tau, X, RL, alpha, alin, qdd, &ex);
   if (mode == 2) {
     if (!valid) return;
     float* o = out + (size_t)i * 18;

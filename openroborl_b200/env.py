@@ -23,7 +23,11 @@ TASK_DEFAULTS = dict(
 # physics model of this repo (DESIGN.md "physics model"); gravity from quadruped_gym_env.py:200
 PHYS_DEFAULTS = dict(gravity_z=-10.0, contact_kn=1.0e5, contact_bn=500.0, contact_d0=0.002, contact_bt=3000.0,
                      limit_k=1000.0, limit_d=2.0, limit_e0=0.01, mu_plane=1.0, margin_factor=0.02,
-                     max_coordinate_velocity=100.0)
+                     max_coordinate_velocity=100.0, joint_friction_k=0.5)
+# minitaur_env_randomizer_config.py:22-36 ("all_params"), keys in the reference's sorted sampling order
+RANDOMIZER_DEFAULTS = {"battery": (14.0, 16.8), "inertia": (0.5, 1.5), "joint friction": (0.0, 0.05), "latency": (0.0, 0.04),
+                       "lateral friction": (0.5, 1.25), "mass": (0.8, 1.2), "motor friction": (0.0, 0.05),
+                       "motor strength": (0.8, 1.2)}
 
 _INT_FIELDS = ("clip", "warmup", "substep_counter", "step_counter", "env_step_counter", "episode")
 _F64_FIELDS = ("time_offset", "prev_phase")
@@ -31,7 +35,8 @@ _FIELD_SHAPES = dict(
     pos=(3,), quat=(4,), q=(12,), lin=(3,), ang=(3,), qd=(12,), filt_x=(2, 12), filt_y=(2, 12), prev_filtered=(12,),
     ring1=(12,), ring2=(12,), imu_hist=(3, 4), act_hist=(3, 12), ang_hist=(3, 12), ref_pose=(19,), ref_vel=(18,),
     origin_pos=(3,), origin_rot=(4,), time_offset=(), prev_phase=(), clip=(), warmup=(), substep_counter=(),
-    step_counter=(), env_step_counter=(), episode=(), ep_return=(), obs_quat=(4,), motor_strength=(12,))
+    step_counter=(), env_step_counter=(), episode=(), ep_return=(), obs_quat=(4,), motor_strength=(12,),
+    rand_params=(12,))
 
 
 class OrlError(RuntimeError):
@@ -48,7 +53,8 @@ class _DevView(object):
 
 class BatchedImitationEnv(object):
     def __init__(self, robot="laikago", motions=None, num_robot=1, device=0, seed=0, gid0=0, auto_reset=False,
-                 max_episode_steps=600, task=None, phys=None, urdf_search_path=None, action_repeat=None):
+                 max_episode_steps=600, task=None, phys=None, urdf_search_path=None, action_repeat=None,
+                 enable_randomizer=False, randomizer_ranges=None):
         if not motions:
             raise ValueError("No reference motions specified.")           # imitation_task.py:583-584
         self._lib = _abi.load_library()
@@ -80,8 +86,16 @@ class BatchedImitationEnv(object):
                   "root_pose_err_scale", "root_velocity_err_scale", "dist_fail_threshold", "rot_fail_threshold"):
             setattr(cfg, k, float(self.task[k]))
         for k in ("gravity_z", "contact_kn", "contact_bn", "contact_d0", "contact_bt", "limit_k", "limit_d", "limit_e0",
-                  "max_coordinate_velocity"):
+                  "max_coordinate_velocity", "joint_friction_k", "mu_plane"):
             setattr(cfg, k, float(self.phys[k]))
+        # domain randomizer (run.py:205-211 enables it in train mode only)
+        self.enable_randomizer = bool(enable_randomizer)
+        self.randomizer_ranges = dict(RANDOMIZER_DEFAULTS, **(randomizer_ranges or {}))
+        if sorted(self.randomizer_ranges) != sorted(RANDOMIZER_DEFAULTS):
+            raise ValueError("unknown randomizer parameter: %s" % sorted(set(self.randomizer_ranges) - set(RANDOMIZER_DEFAULTS)))
+        cfg.enable_randomizer = int(self.enable_randomizer)
+        for i, name in enumerate(sorted(RANDOMIZER_DEFAULTS)):
+            cfg.rand_lo[i], cfg.rand_hi[i] = [float(v) for v in self.randomizer_ranges[name]]
         self.cfg = cfg
         self.env_time_step = cfg.env_time_step
         self._h = C.c_void_p()
@@ -272,6 +286,13 @@ class BatchedImitationEnv(object):
         out = torch.zeros((n, self.model.num_joints, 3), dtype=torch.float32, device=self.device)
         self._check(self._lib.orl_fk(self._h, C.c_void_p(pose.data_ptr()), n, C.c_void_p(out.data_ptr()), self._stream()))
         return out.cpu().numpy()
+
+    def set_dynamics_rand(self, rand=None):
+        """Randomizer values [n][12] (`rand_params` layout) for the next mass_matrix / inverse_dynamics /
+        forward_dynamics calls; None restores the model's own parameters."""
+        self._parity_rand = None if rand is None else self._dev(rand, 12)
+        ptr = None if rand is None else C.c_void_p(self._parity_rand.data_ptr())
+        self._check(self._lib.orl_set_dynamics_rand(self._h, ptr))
 
     def mass_matrix(self, pose):
         pose = self._dev(pose, 19)

@@ -271,11 +271,19 @@ class RobotModel(object):
                 coms = [pc + Rc @ pl.com for pl, Rc, pc, _ in parts]          # in this joint's LINK frame
                 com = sum(pl.mass * cm for (pl, _, _, _), cm in zip(parts, coms)) / m_tot
                 I = np.zeros((3, 3))
+                I_par = np.zeros((3, 3))        # parallel-axis share: scales with the randomised mass ratio
                 for (pl, Rc, pc, _), cm in zip(parts, coms):
                     Rl = Rc @ pl.R_in
                     d = cm - com
-                    I += Rl @ pl.I @ Rl.T + pl.mass * ((d @ d) * np.eye(3) - np.outer(d, d))
-                com_b, I_b = to_body(com), A.T @ I @ A
+                    I_par += pl.mass * ((d @ d) * np.eye(3) - np.outer(d, d))
+                    I += Rl @ pl.I @ Rl.T
+                I = I + I_par
+                com_b, I_b, I_pb = to_body(com), A.T @ I @ A, A.T @ I_par @ A
+                # randomizer bookkeeping (minitaur.py:935-1070): class of the merged links, knee-friction sample
+                classes = {0 if lid in self.chassis_link_ids else 1 for _, _, _, lid in parts}
+                L.rand_class[k] = classes.pop() if len(classes) == 1 else -1
+                L.friction_draw[k] = self.foot_link_ids.index(jid) if jid in self.foot_link_ids else -1
+                L.inertia_par[k][:] = [I_pb[0, 0], I_pb[0, 1], I_pb[0, 2], I_pb[1, 1], I_pb[1, 2], I_pb[2, 2]]
                 L.mass[k] = m_tot
                 self.mass_total += m_tot
                 L.com[k][:] = list(com_b)

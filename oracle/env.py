@@ -19,7 +19,8 @@ from .robots import get_spec, classify_links
 DEFAULT_PHYS = dict(
     gravity=(0.0, 0.0, -10.0),   # quadruped_gym_env.py:200
     kn=1.0e5, bn=500.0, d0=0.002, bt=3000.0, mu_plane=1.0,
-    k_lim=1000.0, d_lim=2.0, e0=0.01, margin_factor=0.02, max_coordinate_velocity=100.0)
+    k_lim=1000.0, d_lim=2.0, e0=0.01, margin_factor=0.02, max_coordinate_velocity=100.0,
+    joint_friction_k=0.5)
 
 # imitation_task.py:45-58 as configured by run.py:58-64
 DEFAULT_TASK = dict(
@@ -39,7 +40,7 @@ TRUE_OBS = 43     # minitaur.py:304-311
 
 class OracleEnv(object):
     def __init__(self, robot_name, urdf_path, clips, num_robot, phys=None, task=None, seed=0,
-                 gid0=0, max_episode_steps=600):
+                 gid0=0, max_episode_steps=600, randomizer=False, randomizer_ranges=None):
         self.spec = get_spec(robot_name)
         self.tree = UrdfTree(urdf_path)
         self.lib = MotionLib(clips)
@@ -49,6 +50,9 @@ class OracleEnv(object):
         self.seed = seed
         self.gid = np.arange(self.N, dtype=np.int64) + gid0
         self.max_episode_steps = max_episode_steps
+        from .randomizer import ALL_PARAMS
+        self.randomizer = bool(randomizer)
+        self.randomizer_ranges = dict(ALL_PARAMS, **(randomizer_ranges or {}))
         t, s = self.tree, self.spec
         assert t.n_dof == 12 and self.lib.frames.shape[1] == 7 + t.n_dof  # imitation_task.py:689-690
         ids = classify_links(s, t.joint_names)
@@ -98,6 +102,14 @@ class OracleEnv(object):
         self.prev_phase = np.zeros(N)
         self.ref_pose = np.zeros((N, 19)); self.ref_vel = np.zeros((N, 18))
         self.motor_strength = np.ones((N, 12))
+        # domain randomizer state (oracle/randomizer.py); identity when it is off
+        nb = t.n_links + 1
+        self.link_mass = np.tile(np.asarray(t.mass, dtype=np.float64), (N, 1))
+        self.inertia_scale = np.ones((N, nb))
+        self.foot_friction = np.full(N, -1.0)            # < 0: the URDF value
+        self.joint_friction = np.zeros((N, 12))          # Coulomb torque limit per URDF joint coordinate
+        self.ctrl_latency = np.zeros(N)                  # sampled, NOT applied (DESIGN.md "out of scope")
+        self.rand_values = None
         self.default_pose = np.concatenate([s.init_pos, s.init_quat,
                                             (s.init_motor + s.joint_offset) * s.joint_dir])  # minitaur.py:1190-1194
         self._urdf_from_motor = np.argsort(self.motor_q)
@@ -196,7 +208,7 @@ class OracleEnv(object):
         return xf.calc_heading(xf.quaternion_multiply(rot, inv_def))
 
     # ---- reset (quadruped_gym_env.py:63-104, minitaur.py:232-278, imitation_task.py:166-199) ----
-    def reset(self, mask=None, draws=None, time_offset=None):
+    def reset(self, mask=None, draws=None, time_offset=None, rand_uniforms=None):
         N, s = self.N, self.spec
         m = np.ones(N, dtype=bool) if mask is None else np.asarray(mask, dtype=bool)
         mm = m[:, None]
@@ -222,6 +234,23 @@ class OracleEnv(object):
         self.imu_hist = np.where(m[:, None, None], imu[:, None], self.imu_hist)
         self.act_hist = np.where(m[:, None, None], la[:, None], self.act_hist)
         self.ang_hist = np.where(m[:, None, None], ma[:, None], self.ang_hist)
+        # -- randomizers (minitaur.py:273-276)
+        if self.randomizer:
+            from . import randomizer as orand
+            u = philox.randomizer_draws(self.seed, self.gid, self.episode) if rand_uniforms is None else np.asarray(rand_uniforms)
+            vals = orand.sample(u, params=self.randomizer_ranges)
+            a = orand.apply(vals, self.ids, np.asarray(self.tree.mass, dtype=np.float64), None)
+            self.link_mass = np.where(mm, a["mass"], self.link_mass)
+            self.inertia_scale = np.where(mm, a["inertia_scale"], self.inertia_scale)
+            self.motor_strength = np.where(mm, a["motor_strength"], self.motor_strength)
+            self.foot_friction = np.where(m, a["foot_friction"], self.foot_friction)
+            self.ctrl_latency = np.where(m, a["latency"], self.ctrl_latency)
+            jf = np.zeros((N, 12))
+            for link_id in range(a["joint_friction"].shape[1]):
+                if self.tree.movable[link_id]:
+                    jf[:, self.tree.qidx[link_id]] = a["joint_friction"][:, link_id]
+            self.joint_friction = np.where(mm, jf, self.joint_friction)
+            self.rand_values = vals
         # -- ImitationTask.reset
         if draws is None:
             draws = philox.reset_draws(self.seed, self.gid, self.episode, self.lib.n_clips)
@@ -317,6 +346,9 @@ class OracleEnv(object):
         lo, up, damp = t.lower[self.revolute_links], t.upper[self.revolute_links], t.damping[self.revolute_links]
         e = np.maximum(0.0, lo - self.q) - np.maximum(0.0, self.q - up)
         tau = tau + p["k_lim"] * e - p["d_lim"] * np.minimum(1.0, np.abs(e) / p["e0"]) * self.qd - damp * self.qd
+        # set_joint_friction (minitaur.py:1063-1070): Bullet's velocity motor with a force limit, here a regularised
+        # Coulomb torque  -clip(k qd, -F, F)
+        tau = tau - np.clip(p["joint_friction_k"] * self.qd, -self.joint_friction, self.joint_friction)
         return tau
 
     def contact_forces(self, k, nu):
@@ -348,7 +380,8 @@ class OracleEnv(object):
             sc = np.minimum(1.0, d / p["d0"])
             fn = np.maximum(0.0, p["kn"] * d - p["bn"] * sc * V[:, 2])
             vt = np.sqrt(V[:, 0] ** 2 + V[:, 1] ** 2)
-            ct = np.minimum(p["bt"], self.cp_mu[c] * fn / np.maximum(vt, 1e-9))
+            mu = np.where(self.cp_foot[c] & (self.foot_friction >= 0), self.foot_friction * p["mu_plane"], self.cp_mu[c])   # set_foot_friction
+            ct = np.minimum(p["bt"], mu * fn / np.maximum(vt, 1e-9))
             cn = np.where(fn > 0.0, p["kn"] * dt + p["bn"] * sc, 0.0)
             F = np.stack([-ct * V[:, 0], -ct * V[:, 1], fn], axis=-1)
             D = np.stack([ct, ct, cn], axis=-1)
@@ -362,8 +395,8 @@ class OracleEnv(object):
         t = self.tree
         nu = np.concatenate([self.ang, self.lin, self.qd], axis=-1)
         k = t.fk(self.pos, self.quat, self.q)
-        M = t.mass_matrix(self.pos, self.quat, self.q)
-        C = t.bias(self.pos, self.quat, self.q, nu, self.phys["gravity"], k=k)
+        M = t.mass_matrix(self.pos, self.quat, self.q, mass=self.link_mass, inertia_scale=self.inertia_scale)
+        C = t.bias(self.pos, self.quat, self.q, nu, self.phys["gravity"], mass=self.link_mass, inertia_scale=self.inertia_scale, k=k)
         gen_c, W, _ = self.contact_forces(k, nu)
         rhs = gen_c - C
         rhs[:, 6:] += tau_joint

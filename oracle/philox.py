@@ -53,3 +53,16 @@ def reset_draws(seed, gid, episode, n_clips):
     clip = ((a[..., 2].astype(np.uint64) * np.uint64(n_clips)) >> np.uint64(32)).astype(np.int64)
     u_time = u01_53(b[..., 0], b[..., 1])
     return u_rsi, clip, u_time
+
+
+def randomizer_draws(seed, gid, episode, n=28):
+    """Uniforms of the domain randomizer of one reset: Philox blocks 2.. of the (robot, episode) stream, one 32-bit
+    word per draw, u = (word + 0.5) / 2^32 (the product's keying; the reference uses a RandomState per robot)."""
+    gid = np.asarray(gid, dtype=np.uint32)
+    episode = np.asarray(episode, dtype=np.uint32)
+    key = np.stack([np.full(gid.shape, seed & 0xFFFFFFFF, dtype=np.uint32),
+                    np.full(gid.shape, (seed >> 32) & 0xFFFFFFFF, dtype=np.uint32)], axis=-1)
+    z = np.zeros_like(gid)
+    words = [philox4x32(np.stack([gid, episode, z + np.uint32(2 + b), z], axis=-1), key) for b in range((n + 3) // 4)]
+    w = np.concatenate(words, axis=-1)[..., :n]
+    return (w.astype(np.float64) + 0.5) * (1.0 / 4294967296.0)

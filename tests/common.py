@@ -42,16 +42,18 @@ def load_policy(name):
     return policy
 
 
-def make_oracle(robot, clip_names, N, seed=0, gid0=0, max_episode_steps=600, task=None, phys=None):
+def make_oracle(robot, clip_names, N, seed=0, gid0=0, max_episode_steps=600, task=None, phys=None, randomizer=False):
     from oracle.env import OracleEnv
     return OracleEnv(robot, URDF[robot], golden_clips_raw(clip_names), N, seed=seed, gid0=gid0,
-                     max_episode_steps=max_episode_steps, task=task, phys=phys)
+                     max_episode_steps=max_episode_steps, task=task, phys=phys, randomizer=randomizer)
 
 
-def make_product(robot, clip_names, N, seed=0, gid0=0, max_episode_steps=600, auto_reset=False, task=None, phys=None):
+def make_product(robot, clip_names, N, seed=0, gid0=0, max_episode_steps=600, auto_reset=False, task=None, phys=None,
+                 randomizer=False):
     from openroborl_b200.env import BatchedImitationEnv
     return BatchedImitationEnv(robot, product_clips(clip_names), num_robot=N, seed=seed, gid0=gid0,
-                               max_episode_steps=max_episode_steps, auto_reset=auto_reset, task=task, phys=phys)
+                               max_episode_steps=max_episode_steps, auto_reset=auto_reset, task=task, phys=phys,
+                               enable_randomizer=randomizer)
 
 
 def oracle_phys_from_product(phys):
@@ -59,7 +61,27 @@ def oracle_phys_from_product(phys):
     return dict(gravity=(0.0, 0.0, phys["gravity_z"]), kn=phys["contact_kn"], bn=phys["contact_bn"], d0=phys["contact_d0"],
                 bt=phys["contact_bt"], mu_plane=phys["mu_plane"], k_lim=phys["limit_k"], d_lim=phys["limit_d"],
                 e0=phys["limit_e0"], margin_factor=phys["margin_factor"],
-                max_coordinate_velocity=phys["max_coordinate_velocity"])
+                max_coordinate_velocity=phys["max_coordinate_velocity"], joint_friction_k=phys["joint_friction_k"])
+
+
+def load_rand_params(oracle, rp):
+    """Product randomizer record (orl_state_layout.rand_params) -> the oracle's per-robot physical parameters."""
+    ids, t = oracle.ids, oracle.tree
+    N, nb = oracle.N, t.n_links + 1
+    rm, ri = np.ones((N, nb)), np.ones((N, nb))
+    for i in ids["chassis"]:
+        rm[:, i + 1] = rp[:, 0]; ri[:, i + 1] = rp[:, 2]
+    for i in list(ids["leg"]) + list(ids["motor"]):
+        rm[:, i + 1] = rp[:, 1]; ri[:, i + 1] = rp[:, 3]
+    oracle.link_mass = rm * np.asarray(t.mass, dtype=np.float64)[None, :]
+    oracle.inertia_scale = ri
+    oracle.ctrl_latency = rp[:, 4].copy()
+    oracle.foot_friction = np.where(rp[:, 5] >= 0, rp[:, 5] / oracle.phys["mu_plane"], -1.0)
+    jf = np.zeros((N, 12))
+    knees = [i for i in ids["foot"] if t.movable[i]]               # one per leg, URDF leg order
+    for leg, link_id in enumerate(knees):
+        jf[:, t.qidx[link_id]] = rp[:, 6 + leg]
+    oracle.joint_friction = jf
 
 
 def sync_oracle_from_product(oracle, st):
@@ -83,6 +105,8 @@ def sync_oracle_from_product(oracle, st):
     oracle.prev_phase = f(st["prev_phase"])
     oracle.ref_pose, oracle.ref_vel = f(st["ref_pose"]), f(st["ref_vel"])
     oracle.motor_strength = f(st["motor_strength"])
+    if "rand_params" in st:
+        load_rand_params(oracle, f(st["rand_params"]))
     # observation ring: entry 0 = current true state, entries 1/2 carry the delayed motor angles
     N = oracle.N
     oracle.hist = np.zeros((N, 4, 43))

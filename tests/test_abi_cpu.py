@@ -25,12 +25,17 @@ def test_every_declared_symbol_is_exported_and_bound():
     assert lib.orl_abi_version() == _abi.ORL_ABI_VERSION
 
 
-def test_struct_sizes_match_header():
-    """Guard the ctypes mirrors against drift: sizes derived from the header's field lists."""
-    assert ctypes.sizeof(_abi.OrlContactPoint) == 8 * 4
-    assert ctypes.sizeof(_abi.OrlLegModel) == (27 + 9 + 3 + 9 + 18 + 9 + 15 + 3 + 1 + 2 + 6 + 1) * 4 + _abi.MAX_CP * 32
-    assert ctypes.sizeof(_abi.OrlRobotModel) == (1 + 6 + 3 + 4 + 1) * 4 + 4 * ctypes.sizeof(_abi.OrlLegModel) + (1 + 32 + 32 + 96) * 4
-    assert ctypes.sizeof(_abi.OrlStateLayout) == 30 * 4
+def test_struct_sizes_match_header(tmp_path):
+    """Guard the ctypes mirrors against drift: sizeof() of every struct as the C compiler sees include/orl.h."""
+    import subprocess
+    src = tmp_path / "sizes.c"
+    src.write_text('#include <stdio.h>\n#include "orl.h"\nint main(void) { printf("%zu %zu %zu %zu %zu\\n", sizeof(orl_config), '
+                   'sizeof(orl_contact_point), sizeof(orl_leg_model), sizeof(orl_robot_model), sizeof(orl_state_layout)); return 0; }\n')
+    exe = tmp_path / "sizes"
+    subprocess.check_call(["gcc", "-I", os.path.join(common.ROOT, "include"), "-o", str(exe), str(src)])
+    sizes = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    mirrors = [_abi.OrlConfig, _abi.OrlContactPoint, _abi.OrlLegModel, _abi.OrlRobotModel, _abi.OrlStateLayout]
+    assert sizes == [ctypes.sizeof(m) for m in mirrors]
 
 
 def test_null_handle_calls_fail_cleanly():

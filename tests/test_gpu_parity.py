@@ -248,6 +248,110 @@ def test_non_finite_state_ends_the_episode():
     env.close()
 
 
+# ---- (f2) domain randomizer ----------------------------------------------------------------------------------
+@pytest.mark.parametrize("robot,clip", [("laikago", "laikago_pace"), ("mini_cheetah", "minicheetah_trot")])
+def test_randomizer_reset_values_match_oracle(robot, clip):
+    """Same Philox draws -> same sampled parameters (reference arithmetic: oracle/randomizer.py, pinned to the
+    reference class by tests/golden/ref_randomizer_kat.npz)."""
+    from oracle import randomizer as orand
+    N = 256
+    env = common.make_product(robot, [clip], N, seed=11, randomizer=True)
+    orc = common.make_oracle(robot, [clip], N, seed=11, randomizer=True)
+    for episode in range(2):
+        env.reset(); orc.reset()
+        st = env.get_state()
+        rp = st["rand_params"].astype(np.float64)
+        v = orc.rand_values
+        tol = dict(rtol=2e-7, atol=1e-9)
+        assert np.allclose(rp[:, 0], v["mass"][:, 0], **tol) and np.allclose(rp[:, 1], v["mass"][:, 1], **tol)
+        assert np.allclose(rp[:, 2], v["inertia"][:, 0], **tol) and np.allclose(rp[:, 3], v["inertia"][:, 1], **tol)
+        assert np.allclose(rp[:, 4], v["latency"][:, 0], **tol)
+        assert np.allclose(rp[:, 5], v["lateral friction"][:, 0] * env.phys["mu_plane"], **tol)
+        assert np.allclose(rp[:, 6:10], v["joint friction"][:, 0:8:2], **tol)          # knee of leg l <- sample 2l
+        assert np.allclose(st["motor_strength"], v["motor strength"], **tol)
+        # the record maps back onto the oracle's physical parameters
+        o2 = common.make_oracle(robot, [clip], N, seed=11)
+        common.load_rand_params(o2, rp)
+        assert np.allclose(o2.link_mass, orc.link_mass, rtol=3e-7) and np.allclose(o2.inertia_scale, orc.inertia_scale, rtol=3e-7)
+        assert np.allclose(o2.joint_friction, orc.joint_friction, rtol=3e-7, atol=1e-9)
+        assert np.allclose(o2.foot_friction, orc.foot_friction, rtol=3e-7)
+        for name, (lo, hi) in orand.ALL_PARAMS.items():
+            assert v[name].min() >= lo and v[name].max() <= hi
+    # a second episode draws new values; a disabled randomizer leaves the defaults
+    off = common.make_product(robot, [clip], 8, seed=11)
+    off.reset()
+    r0 = off.get_state()["rand_params"]
+    assert np.array_equal(r0[:, :4], np.ones((8, 4), np.float32)) and (r0[:, 5] == -1).all() and (r0[:, 6:10] == 0).all()
+    env.close(); off.close()
+
+
+def test_randomized_dynamics_match_oracle():
+    """Mass matrix / inverse dynamics / forward dynamics with per-robot masses, inertias, foot friction."""
+    N = 128
+    env = common.make_product("laikago", ["laikago_pace"], N, seed=3, randomizer=True)
+    orc = common.make_oracle("laikago", ["laikago_pace"], N, seed=3, randomizer=True)
+    env.reset(); orc.reset()
+    st = env.get_state()
+    common.sync_oracle_from_product(orc, st)
+    rng = np.random.default_rng(0)
+    pose = np.concatenate([st["pos"], st["quat"], st["q"]], axis=1)
+    pose[:, 2] -= rng.uniform(0.0, 0.004, size=N).astype(np.float32)         # push the feet into the ground
+    vel = rng.normal(scale=0.5, size=(N, 18)).astype(np.float32)
+    env.set_dynamics_rand(st["rand_params"])
+    M = env.mass_matrix(pose)
+    t = orc.tree
+    Mo = t.mass_matrix(pose[:, 0:3].astype(np.float64), pose[:, 3:7].astype(np.float64), pose[:, 7:].astype(np.float64),
+                       mass=orc.link_mass, inertia_scale=orc.inertia_scale)
+    Mo = Mo[:, PERM][:, :, PERM]                                              # oracle order [ang, lin, q] -> interface [lin, ang, q]
+    assert np.abs(M - Mo).max() <= 1e-4 * np.abs(Mo).max()
+    leg = np.abs(Mo[:, 6:, 6:]).max()
+    assert np.abs(M - Mo)[:, 6:, 6:].max() <= 1e-4 * leg                      # the small leg blocks on their own scale
+    # and it is NOT the un-randomised matrix
+    env.set_dynamics_rand(None)
+    assert np.abs(env.mass_matrix(pose) - Mo).max() > 1e-2 * np.abs(Mo).max()
+    env.set_dynamics_rand(st["rand_params"])
+    # forward dynamics with contact
+    tau = rng.normal(scale=3.0, size=(N, 12)).astype(np.float32)
+    acc = env.forward_dynamics(pose, vel, tau)
+    orc.pos, orc.quat, orc.q = [pose[:, a:b].astype(np.float64) for a, b in ((0, 3), (3, 7), (7, 19))]
+    orc.lin, orc.ang, orc.qd = [vel[:, a:b].astype(np.float64) for a, b in ((0, 3), (3, 6), (6, 18))]
+    acc_o = orc.forward_dynamics(tau.astype(np.float64))[:, PERM]
+    assert np.abs(acc - acc_o).max() <= 1e-4 * np.abs(acc_o).max()          # same criterion as the nominal test
+    err = np.abs(acc - acc_o).max(axis=1) / (np.abs(acc_o).max(axis=1) + 1.0)
+    assert np.median(err) < 2e-5
+    env.set_dynamics_rand(None)
+    env.close()
+
+
+def test_randomized_control_step_matches_oracle():
+    N = 128
+    env = common.make_product("laikago", ["laikago_pace"], N, seed=5, randomizer=True)
+    orc = common.make_oracle("laikago", ["laikago_pace"], N, seed=5, randomizer=True)
+    env.reset(); orc.reset()
+    rng = np.random.default_rng(2)
+    for step in range(3):
+        common.sync_oracle_from_product(orc, env.get_state())
+        act = rng.normal(scale=0.2, size=(N, 12)).astype(np.float32)
+        o, r, d = env.step(torch.as_tensor(act, device=env.device))
+        oo, ro, do = orc.step(act.astype(np.float64))
+        o, r = o.cpu().numpy(), r.cpu().numpy()
+        st = env.get_state()
+        ok = np.abs(st["qd"] - orc.qd).max(axis=1) < 2e-2
+        assert ok.mean() > 0.95
+        assert np.abs(r - ro)[ok].max() <= 1e-4 and np.median(np.abs(r - ro)) <= 5e-6
+        assert np.abs(st["q"] - orc.q)[ok].max() <= 2e-4 and np.abs(st["pos"] - orc.pos)[ok].max() <= 1e-4
+    # the randomised robots really move differently from the nominal ones
+    nominal = common.make_product("laikago", ["laikago_pace"], N, seed=5)
+    nominal.reset()
+    s0 = env.get_state()
+    keep = {k: s0[k] for k in ("pos", "quat", "q", "lin", "ang", "qd")}
+    nominal.set_state(dict(keep)); env.set_state(dict(keep))
+    z = torch.zeros((N, 12), device=env.device)
+    nominal.step(z); env.step(z)
+    assert np.abs(nominal.get_state()["q"] - env.get_state()["q"]).max() > 1e-3
+    env.close(); nominal.close()
+
+
 def test_time_limit_and_termination_thresholds(laikago):
     env, orc = laikago
     env.reset(); orc.reset()
