@@ -252,7 +252,8 @@ class LocomotionGymEnv(object):
         tp = dict(TASK_DEFAULTS, **p0)
         self._cuda = BatchedImitationEnv(robot[0].name_robot, clips, num_robot=self.num_robot, device=device, seed=seed,
                                          auto_reset=False, max_episode_steps=2 ** 30, task=tp,
-                                         urdf_search_path=urdf_search_path)
+                                         urdf_search_path=urdf_search_path,
+                                         enable_randomizer=bool(robot[0]._enable_randomizer))   # minitaur.py:273-276
         self._num_action_repeat = robot[0].action_repeat
         self._sim_time_step = sim["sim_time_step_s"]
         self._env_time_step = self._num_action_repeat * self._sim_time_step          # :177

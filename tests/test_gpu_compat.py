@@ -15,6 +15,25 @@ def motion_file(tmp_path):
     return str(p)
 
 
+def test_train_mode_randomizes_the_dynamics_at_every_reset(motion_file):
+    """run.py:205-211: enable_randomizer is on in train mode; Minitaur.reset -> randomize_env (minitaur.py:273-276)."""
+    from openroborl_b200 import compat
+    env = compat.build_env("imitation_learning_laikago", num_robot=16, num_parallel_envs=1, mode="train",
+                           enable_randomizer=True, motion_files=[motion_file], seed=4)
+    env.reset()
+    cu = env._gym_env._cuda
+    r1 = cu.get_state()["rand_params"].copy()
+    assert (r1[:, 0] >= 0.8).all() and (r1[:, 0] <= 1.2).all() and np.ptp(r1[:, 0]) > 0.05        # mass
+    assert (r1[:, 2] >= 0.5).all() and (r1[:, 2] <= 1.5).all()                                    # inertia
+    assert (r1[:, 5] >= 0.5).all() and (r1[:, 5] <= 1.25).all()                                   # lateral friction
+    assert (r1[:, 6:10] >= 0).all() and (r1[:, 6:10] <= 0.05).all()                               # knee friction
+    env.reset()
+    r2 = cu.get_state()["rand_params"]
+    assert not np.array_equal(r1, r2)                                                             # new draw per episode
+    s = cu.get_state()["motor_strength"]
+    assert (s >= 0.8).all() and (s <= 1.2).all() and np.ptp(s) > 0.1
+
+
 def test_build_env_contract(motion_file):
     from openroborl_b200 import compat
     env = compat.build_env("imitation_learning_laikago", num_robot=3, num_parallel_envs=1, mode="test",
