@@ -33,6 +33,11 @@ struct __align__(16) DevLeg {
   float4 bb[4][2];     // per body (0,1,2,base): body-frame bounding box of its NON-primary points: (centre xyz, max radius), (half extents, -)
   DevCp cp[ORL_DEV_MAX_CP];
 };
+// The four lanes of a quad read the same field of four different legs with one LDS.128: the legs' copies have to
+// fall into different 16-byte bank groups (a 1600-byte DevLeg put legs 0/2 and 1/3 on the same banks and doubled
+// the shared-memory wavefronts of every model load, profiles/r01_v4_step_kernel.md).
+static_assert((sizeof(DevLeg) / 16) % 8 != 0 && (sizeof(DevLeg) / 16) % 8 != 4, "DevLeg stride maps two legs onto the same shared-memory banks");
+
 struct __align__(16) DevModel {
   float4 b0;           // base mass, Ixx, Ixy, Ixz
   float4 b1;           // Iyy, Iyz, Izz, max_angle_change

@@ -155,7 +155,10 @@ ORL_DI Q4 ldq4(float4 v) { return q4(v.x, v.y, v.z, v.w); }
 // ImitationTask.build_target_obs (imitation_task.py:254-301): lane j of the quad builds frame j.
 ORL_DI void build_obs(float* S, float* O, const DevEnv& E, int leg) {
   const DevCfg& C = E.cfg;
-  for (int i = leg; i < 84; i += 4) O[i] = S[S_IMU + i];
+  static_assert(S_IMU % 4 == 0 && ORL_STRIDE % 4 == 0 && ORL_OBS_SIZE % 4 == 0, "history block must be float4 aligned");
+#pragma unroll 1
+  for (int i = leg; i < 21; i += 4)           // 84 floats of sensor history: the quad copies 21 float4
+    reinterpret_cast<float4*>(O)[i] = reinterpret_cast<const float4*>(S + S_IMU)[i];
   const RefFrame F = load_ref_frame(S, C);
   const double t0 = motion_time(S, C);
   const float3 ref_base = ld3(S + S_REFPOSE);
