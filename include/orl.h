@@ -217,6 +217,11 @@ int orl_motion_lookup(orl_env* env, const int32_t* clip_dev, const double* time_
 int orl_fk(orl_env* env, const float* pose_dev, int32_t n, float* com_dev, void* stream);
 /* Joint-space inertia matrix (CRBA), generalised-velocity order [root lin(3), root ang(3), joints(12)]:
  * pose_dev [n][19] -> M_dev [n][18][18].  Oracle: pybullet.calculateMassMatrix (north_star). */
+/* Observation history behind the randomised control latency (minitaur.py:313-357), for tests and checkpoints:
+ * ring_q [n][ORL_LAT_RING][12] true motor angles, ring_b [n][ORL_LAT_RING][8] (orientation rel. to init (4), body-frame
+ * angular velocity (3), pad); entry E of a robot sits in slot E % ORL_LAT_RING, E = substep counter + 1.  Either may be NULL. */
+#define ORL_LAT_RING 42
+int orl_get_latency_rings_host(orl_env* env, float* ring_q, float* ring_b);
 /* Randomizer values [n][12] (layout of orl_state_layout.rand_params) used by the three dynamics entry points below;
  * NULL (default) = the model's own masses, inertias and friction. */
 int orl_set_dynamics_rand(orl_env* env, const float* rand_dev);

@@ -281,9 +281,17 @@ extern "C" int orl_create(const orl_config* cfg, const orl_robot_model* model, o
   CUDA_TRY(e, cudaMalloc(&e->d_mask, (size_t)N));
   CUDA_TRY(e, cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   for (int i = 0; i < ORL_D2H_CHUNKS; ++i) CUDA_TRY(e, cudaEventCreateWithFlags(&e->ev_chunk[i], cudaEventDisableTiming));
-  CUDA_TRY(e, cudaFuncSetAttribute(orl_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ORL_SMEM_BYTES));
+  CUDA_TRY(e, cudaFuncSetAttribute(orl_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ORL_SMEM_BYTES));
+  CUDA_TRY(e, cudaFuncSetAttribute(orl_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ORL_SMEM_BYTES));
   CUDA_TRY(e, cudaFuncSetAttribute(orl_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ORL_SMEM_BYTES));
   e->dev.state = e->d_state; e->dev.model = e->d_model; e->dev.stats = e->d_stats;
+  e->dev.ring_q = nullptr; e->dev.ring_b = nullptr;
+  if (cfg->enable_randomizer) {      // observation history for the randomised control latency
+    CUDA_TRY(e, cudaMalloc(&e->dev.ring_q, (size_t)N * ORL_LAT_RING * 12 * sizeof(float)));
+    CUDA_TRY(e, cudaMalloc(&e->dev.ring_b, (size_t)N * ORL_LAT_RING * 8 * sizeof(float)));
+    CUDA_TRY(e, cudaMemset(e->dev.ring_q, 0, (size_t)N * ORL_LAT_RING * 12 * sizeof(float)));
+    CUDA_TRY(e, cudaMemset(e->dev.ring_b, 0, (size_t)N * ORL_LAT_RING * 8 * sizeof(float)));
+  }
   memset(&e->dev.mt, 0, sizeof(e->dev.mt));
   fill_dev_cfg(e);
   return ORL_OK;
@@ -298,7 +306,7 @@ extern "C" int orl_destroy(orl_env* e) {
   if (!e) return ORL_OK;
   cudaSetDevice(e->device);
   free_motions(e);
-  cudaFree(e->d_state); cudaFree(e->d_model); cudaFree(e->d_stats);
+  cudaFree(e->d_state); cudaFree(e->d_model); cudaFree(e->d_stats); cudaFree(e->dev.ring_q); cudaFree(e->dev.ring_b);
   cudaFreeHost(e->p_act); cudaFreeHost(e->p_obs); cudaFreeHost(e->p_rew); cudaFreeHost(e->p_done); cudaFreeHost(e->p_mask);
   cudaFree(e->d_act); cudaFree(e->d_obs); cudaFree(e->d_rew); cudaFree(e->d_done); cudaFree(e->d_mask);
   for (int i = 0; i < ORL_D2H_CHUNKS; ++i) if (e->ev_chunk[i]) cudaEventDestroy(e->ev_chunk[i]);
@@ -473,7 +481,8 @@ extern "C" int orl_step(orl_env* e, const float* actions_dev, float* obs_dev, fl
   if (!actions_dev || !obs_dev || !reward_dev || !done_dev) return fail(e, ORL_ERR_INVALID, "null buffer");
   if ((uintptr_t)obs_dev & 15) return fail(e, ORL_ERR_INVALID, "observation buffer must be 16-byte aligned");
   const int blocks = (e->cfg.num_robot + ORL_ROBOTS_PER_BLOCK - 1) / ORL_ROBOTS_PER_BLOCK;
-  orl_step_kernel<<<blocks, ORL_BLOCK_THREADS, ORL_SMEM_BYTES, (cudaStream_t)stream>>>(e->dev, actions_dev, obs_dev, reward_dev, done_dev);
+  if (e->dev.ring_q) orl_step_kernel<true><<<blocks, ORL_BLOCK_THREADS, ORL_SMEM_BYTES, (cudaStream_t)stream>>>(e->dev, actions_dev, obs_dev, reward_dev, done_dev);
+  else orl_step_kernel<false><<<blocks, ORL_BLOCK_THREADS, ORL_SMEM_BYTES, (cudaStream_t)stream>>>(e->dev, actions_dev, obs_dev, reward_dev, done_dev);
   return check_launch(e, "orl_step_kernel");
 }
 
@@ -653,6 +662,16 @@ static int dyn_call(orl_env* e, int mode, const float* pose, const float* vel, c
   if (mode == 0) CUDA_TRY(e, cudaMemsetAsync(out, 0, (size_t)n * 324 * sizeof(float), (cudaStream_t)stream));
   orl_dyn_kernel<<<(n * 4 + ORL_DYN_BLOCK - 1) / ORL_DYN_BLOCK, ORL_DYN_BLOCK, 0, (cudaStream_t)stream>>>(e->d_model, e->dev.cfg.phys, mode, pose, vel, in, e->parity_rand, n, out);
   return check_launch(e, "orl_dyn_kernel");
+}
+extern "C" int orl_get_latency_rings_host(orl_env* e, float* ring_q, float* ring_b) {
+  if (!e) return ORL_ERR_INVALID;
+  if (!e->dev.ring_q) return fail(e, ORL_ERR_INVALID, "the observation rings only exist when the randomizer is enabled");
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  CUDA_TRY(e, cudaDeviceSynchronize());
+  const size_t n = (size_t)e->cfg.num_robot * ORL_LAT_RING;
+  if (ring_q) CUDA_TRY(e, cudaMemcpy(ring_q, e->dev.ring_q, n * 12 * sizeof(float), cudaMemcpyDeviceToHost));
+  if (ring_b) CUDA_TRY(e, cudaMemcpy(ring_b, e->dev.ring_b, n * 8 * sizeof(float), cudaMemcpyDeviceToHost));
+  return ORL_OK;
 }
 extern "C" int orl_set_dynamics_rand(orl_env* e, const float* rand_dev) {
   if (!e) return ORL_ERR_INVALID;

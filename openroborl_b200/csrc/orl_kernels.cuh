@@ -36,7 +36,12 @@ struct DevEnv {
   MotionTables mt;
   DevCfg cfg;
   double* stats;                      // [4]
+  // Randomised control latency (minitaur.py:336-357 with latency in [0, 0.04] s): the last ORL_LAT_RING true
+  // observations of every robot, entry E in slot E % ORL_LAT_RING.  Only allocated when the randomizer is on.
+  float* ring_q;                      // [n][ORL_LAT_RING][12] true motor angles
+  float* ring_b;                      // [n][ORL_LAT_RING][8]  base orientation rel. to the init orientation (4), body-frame angular velocity (3)
 };
+// ORL_LAT_RING (orl.h) = 42: latency <= 0.04 s = 40 substeps, entries E-41 .. E are live
 
 // Thread block = ORL_WARPS_PER_BLOCK warps that run the substep loop in lockstep (one barrier per substep): the loop
 // body (~33 KB of SASS) is larger than the SM's 32 KB instruction cache, and warps of one block that stay within the
@@ -284,6 +289,31 @@ ORL_DI void reset_robot(float* S, const DevEnv& E, const DevModel& Mo, int gid, 
     S[S_Q + j] = qj; S[S_QD + j] = vj;
   }
   __syncwarp(qmask);
+  if (E.ring_q) {
+    // Randomised control latency: the observation history restarts with entry 0 = default pose (receive_obs in
+    // Minitaur.reset, minitaur.py:265) and entry 1 = synced pose (receive_obs after _sync_sim_model).
+    float* rq_ = E.ring_q + (size_t)(gid - C.gid0) * (ORL_LAT_RING * 12);
+    const double lat = (double)S[S_RAND + 4] / C.sim_dt;
+    const int n = (int)lat;
+    const float al = (float)(lat - (double)n);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int m = __float_as_int(L.j[k].m1.z);
+      const float qm_def = L.j[k].m1.y * L.j[k].m0.y;
+      const float qm_sync = (S[S_Q + 3 * leg + k] - L.j[k].m0.z) * L.j[k].m0.y;
+      rq_[m] = qm_def; rq_[12 + m] = qm_sync;
+      // control observation the first set_act sees: history = [synced, default]
+      S[S_RING2 + m] = n == 0 ? (1.0f - al) * qm_sync + al * qm_def : qm_def;
+    }
+    if (leg == 0) {
+      float4* rb = reinterpret_cast<float4*>(E.ring_b + (size_t)(gid - C.gid0) * (ORL_LAT_RING * 8));
+      const Q4 oq = qmul(ldq(S + S_QUAT), qconj(ldq4(Mo.iquat)));
+      const float3 ow = qrot(qconj(oq), ld3(S + S_ANG));
+      rb[0] = make_float4(0.f, 0.f, 0.f, 1.f); rb[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+      rb[2] = make_float4(oq.x, oq.y, oq.z, oq.w); rb[3] = make_float4(ow.x, ow.y, ow.z, 0.f);
+    }
+    __syncwarp(qmask);
+  }
 }
 
 // Per-lane state advanced by the physics substeps, and the per-step values of the action path.  Everything that
@@ -301,6 +331,9 @@ struct LaneCtl {
   float strength[3];
   float fric[3];             // Coulomb friction torque of this lane's joints (randomizer; 0: none)
   RandLane rl;
+  int lat_n; float lat_a;    // control latency = (lat_n + lat_a) substeps (LAT kernels)
+  int el0;                   // index of the newest observation entry at the first substep of this step (LAT kernels)
+  float* ring_q; float* ring_b;   // this robot's rings (LAT kernels)
   float mac, inv_ar;
   int capture;
   bool first_step;
@@ -308,25 +341,70 @@ struct LaneCtl {
 #define S_OBSW 37           // scratch in the record's padding: body-frame angular velocity of the control observation
 
 // One 1 ms physics substep of this lane's leg (+ the redundantly integrated base).
+ORL_DI void cp_async4(float* smem_dst, const float* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_addr(smem_dst)), "l"(gmem_src) : "memory");
+}
+// Ring slots of the two entries the control observation of entry index `el` blends (minitaur.py:336-357):
+// history[n] and history[n + 1] counted back from the newest entry el; both the oldest entry (0) while the
+// history is still shorter than the latency.
+ORL_DI void lat_slots(int el, int n, int& a, int& b) {
+  const bool oldest = n >= el;              // n + 1 >= len(history), len = el + 1
+  a = oldest ? 0 : (el - n) % ORL_LAT_RING;
+  b = oldest ? 0 : (el - n - 1) % ORL_LAT_RING;
+}
+ORL_DI void obs_base(const LaneDyn& D, const DevModel& Mo, Q4& oq, float3& ow) {
+  oq = qmul(D.quat, qconj(ldq4(Mo.iquat)));                          // minitaur.py:325-331
+  ow = qrot(qconj(oq), D.ang);                                       // :652-672
+}
+
+template <bool LAT>
 ORL_DI void substep(const DevLeg& L, const DevModel& Mo, const PhysParams& P, const LaneCtl& Ctl, LaneDyn& D, float* S, float4* X, int s) {
   const M3 Rb = qmat(D.quat);
+  const int el = Ctl.el0 + s;                                         // LAT: the current true state is observation entry el
+  if (LAT) {
+    asm volatile("cp.async.wait_all;" ::: "memory");                  // prefetched history entries of this substep
+    if ((threadIdx.x & 3) == 0) {
+      Q4 oq; float3 ow;
+      obs_base(D, Mo, oq, ow);
+      float4* rb = reinterpret_cast<float4*>(Ctl.ring_b + (el % ORL_LAT_RING) * 8);
+      rb[0] = make_float4(oq.x, oq.y, oq.z, oq.w); rb[1] = make_float4(ow.x, ow.y, ow.z, 0.f);
+    }
+  }
   const float lerp = (float)(s + 1) * Ctl.inv_ar;
   float tau[3], qm_now[3];
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     const float4 c1 = L.j[k].c1, m0 = L.j[k].m0, m1 = L.j[k].m1;   // (comy comz lower upper) (damping dir offset kp) (kd init motor brad)
     const float strength = Ctl.strength[k];
-    const float qobs = wrap_pi_fast(D.r2[k]);                              // get_motor_angles(): delayed + wrapped
+    const float qm = (D.q[k] - m0.z) * m0.y;                               // :549-553
+    float ctrl = D.r2[k];
+    if (LAT) {
+      const int m = __float_as_int(m1.z);
+      Ctl.ring_q[(el % ORL_LAT_RING) * 12 + m] = qm;                       // receive_obs: entry el (minitaur.py:313-334)
+      const float hA = Ctl.lat_n == 0 ? qm : S[S_RING1 + m], hB = S[S_RING2 + m];
+      ctrl = (1.0f - Ctl.lat_a) * hA + Ctl.lat_a * hB;                      // _get_delay_obs
+    }
+    const float qobs = wrap_pi_fast(ctrl);                                 // get_motor_angles(): delayed + wrapped
     const float prev = Ctl.first_step ? qobs : Ctl.prevf[k];               // minitaur.py:450-453
     float cmd = fmaf(lerp, Ctl.target[k] - prev, prev);                    // :455-456
     cmd = fminf(fmaxf(cmd, qobs - Ctl.mac), qobs + Ctl.mac);               // :706-723
-    const float qm = (D.q[k] - m0.z) * m0.y;                               // :549-553
     const float qdm = D.qd[k] * m0.y;                                      // :575-578
     const float tm = strength * (-1.0f * (m0.w * (qm - cmd)) - m1.x * qdm);   // minitaur_motor.py:163-166
     const float e = fmaxf(0.f, c1.z - D.q[k]) - fmaxf(0.f, D.q[k] - c1.w);
     tau[k] = fmaf(tm, m0.y, fmaf(P.klim, e, -(fmaf(P.dlim, fminf(1.0f, fabsf(e) * P.inv_e0), m0.x)) * D.qd[k]));
     tau[k] -= fminf(fmaxf(P.kfric * D.qd[k], -Ctl.fric[k]), Ctl.fric[k]);     // set_joint_friction (minitaur.py:1063-1070), regularised
     qm_now[k] = qm;
+  }
+  if (LAT) {      // request the two history entries of the NEXT control observation (entry el + 1) into the record's ring slots
+    int a, b;
+    lat_slots(el + 1, Ctl.lat_n, a, b);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int m = __float_as_int(L.j[k].m1.z);
+      if (Ctl.lat_n != 0) cp_async4(S + S_RING1 + m, Ctl.ring_q + a * 12 + m);
+      cp_async4(S + S_RING2 + m, Ctl.ring_q + b * 12 + m);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   }
   float3 alpha, alin; float qdd[3];
   leg_dynamics<true, false, true>(L, Mo, P, Rb, D.pos.z, D.ang, D.lin, D.q, D.qd, tau, X, Ctl.rl, alpha, alin, qdd, nullptr);
@@ -355,7 +433,7 @@ ORL_DI void substep(const DevLeg& L, const DevModel& Mo, const PhysParams& P, co
     D.q[k] = fmaf(P.dt, D.qd[k], D.q[k]);
     D.r2[k] = D.r1[k]; D.r1[k] = qm_now[k];
   }
-  if (s == Ctl.capture) {   // the control observation at the end of the step is 2 substeps old (minitaur.py:336-357)
+  if (!LAT && s == Ctl.capture) {   // the control observation at the end of the step is 2 substeps old (minitaur.py:336-357)
     const Q4 oq = qmul(D.quat, qconj(ldq4(Mo.iquat)));                 // :325-331
     const float3 ow = qrot(qconj(oq), D.ang);                          // :652-672
     stq(S + S_OBSQ, oq); st3(S + S_OBSW, ow);                          // identical in the four lanes of the quad
@@ -368,6 +446,7 @@ ORL_DI void substep(const DevLeg& L, const DevModel& Mo, const PhysParams& P, co
 #ifndef ORL_STEP_MIN_BLOCKS
 #define ORL_STEP_MIN_BLOCKS (8 / ORL_WARPS_PER_BLOCK)
 #endif
+template <bool LAT>
 __global__ void __launch_bounds__(ORL_BLOCK_THREADS, ORL_STEP_MIN_BLOCKS) orl_step_kernel(DevEnv E, const float* __restrict__ actions, float* __restrict__ obs_out,
                                                       float* __restrict__ reward_out, uint8_t* __restrict__ done_out) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -428,6 +507,24 @@ __global__ void __launch_bounds__(ORL_BLOCK_THREADS, ORL_STEP_MIN_BLOCKS) orl_st
   Ctl.first_step = first_step; Ctl.mac = Mo->b1.w;
   const int AR = C.action_repeat;
   Ctl.inv_ar = 1.0f / (float)AR; Ctl.capture = AR - 3;
+  Ctl.lat_n = 0; Ctl.lat_a = 0.f; Ctl.el0 = substep0 + 1; Ctl.ring_q = nullptr; Ctl.ring_b = nullptr;
+  if (LAT) {
+    // entries: 0 = default pose (Minitaur.reset), 1 = synced pose (ImitationTask.reset), 2 + j = after substep j
+    const double lat = (double)S[S_RAND + 4] / C.sim_dt;
+    Ctl.lat_n = (int)lat;                                              // int(latency / time_step)
+    Ctl.lat_a = (float)(lat - (double)Ctl.lat_n);                      // remaining_latency / time_step
+    Ctl.ring_q = E.ring_q + (size_t)robot_c * (ORL_LAT_RING * 12);
+    Ctl.ring_b = E.ring_b + (size_t)robot_c * (ORL_LAT_RING * 8);
+    int a, b;
+    lat_slots(Ctl.el0, Ctl.lat_n, a, b);
+    __syncwarp();                                                      // r1 / r2 were read from these record slots above
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      if (Ctl.lat_n != 0) cp_async4(S + S_RING1 + mi[k], Ctl.ring_q + a * 12 + mi[k]);
+      cp_async4(S + S_RING2 + mi[k], Ctl.ring_q + b * 12 + mi[k]);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
   __syncwarp();
 #ifdef ORL_PROFILE_RARE
   const long long tl0 = clock64();
@@ -436,7 +533,7 @@ __global__ void __launch_bounds__(ORL_BLOCK_THREADS, ORL_STEP_MIN_BLOCKS) orl_st
 #if ORL_WARPS_PER_BLOCK > 1 && !defined(ORL_NO_LOCKSTEP)
     __syncthreads();                       // keep the block's warps in the same code region (shared I-cache lines)
 #endif
-    substep(L, *Mo, P, Ctl, D, S, X, s);
+    substep<LAT>(L, *Mo, P, Ctl, D, S, X, s);
   }
 #ifdef ORL_PROFILE_RARE
   if (lane == 0) {
@@ -453,10 +550,38 @@ __global__ void __launch_bounds__(ORL_BLOCK_THREADS, ORL_STEP_MIN_BLOCKS) orl_st
 #endif
   __syncwarp();
   pos = D.pos; quat = D.quat; lin = D.lin; ang = D.ang;
-  const Q4 obs_q = ldq(S + S_OBSQ);
-  const float3 obs_w = ld3(S + S_OBSW);
 #pragma unroll
   for (int k = 0; k < 3; ++k) { q[k] = D.q[k]; qd[k] = D.qd[k]; r1[k] = D.r1[k]; r2[k] = D.r2[k]; }
+  if (LAT) {
+    // receive_obs after the last substep: entry el of the final state, then the control observation the sensors
+    // read (and the next step starts from) out of the ring with this robot's latency
+    const int el = Ctl.el0 + AR;
+    asm volatile("cp.async.wait_all;" ::: "memory");
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float qm = (q[k] - L.j[k].m0.z) * L.j[k].m0.y;
+      Ctl.ring_q[(el % ORL_LAT_RING) * 12 + mi[k]] = qm;
+      const float hA = Ctl.lat_n == 0 ? qm : S[S_RING1 + mi[k]], hB = S[S_RING2 + mi[k]];
+      r2[k] = (1.0f - Ctl.lat_a) * hA + Ctl.lat_a * hB;
+    }
+    if (leg == 0) {
+      Q4 oq; float3 ow;
+      obs_base(D, *Mo, oq, ow);
+      float4* rb = reinterpret_cast<float4*>(Ctl.ring_b + (el % ORL_LAT_RING) * 8);
+      rb[0] = make_float4(oq.x, oq.y, oq.z, oq.w); rb[1] = make_float4(ow.x, ow.y, ow.z, 0.f);
+      int a, b;
+      lat_slots(el, Ctl.lat_n, a, b);
+      const float4 a0 = Ctl.lat_n == 0 ? rb[0] : reinterpret_cast<const float4*>(Ctl.ring_b + a * 8)[0];
+      const float4 a1 = Ctl.lat_n == 0 ? rb[1] : reinterpret_cast<const float4*>(Ctl.ring_b + a * 8)[1];
+      const float4 b0 = reinterpret_cast<const float4*>(Ctl.ring_b + b * 8)[0], b1 = reinterpret_cast<const float4*>(Ctl.ring_b + b * 8)[1];
+      const float wa = 1.0f - Ctl.lat_a, wb = Ctl.lat_a;              // linear blend of the raw observation vectors
+      stq(S + S_OBSQ, q4(wa * a0.x + wb * b0.x, wa * a0.y + wb * b0.y, wa * a0.z + wb * b0.z, wa * a0.w + wb * b0.w));
+      st3(S + S_OBSW, v3(wa * a1.x + wb * b1.x, wa * a1.y + wb * b1.y, wa * a1.z + wb * b1.z));
+    }
+    __syncwarp();
+  }
+  const Q4 obs_q = ldq(S + S_OBSQ);
+  const float3 obs_w = ld3(S + S_OBSW);
   // ---- write the dynamic state back to the record ---------------------------------------------------
 #pragma unroll
   for (int k = 0; k < 3; ++k) {

@@ -287,6 +287,14 @@ class BatchedImitationEnv(object):
         self._check(self._lib.orl_fk(self._h, C.c_void_p(pose.data_ptr()), n, C.c_void_p(out.data_ptr()), self._stream()))
         return out.cpu().numpy()
 
+    def latency_rings(self):
+        """Observation history behind the randomised control latency: (motor angles [N,42,12], base [N,42,8])."""
+        R = 42
+        rq = np.empty((self.num_robot, R, 12), dtype=np.float32)
+        rb = np.empty((self.num_robot, R, 8), dtype=np.float32)
+        self._check(self._lib.orl_get_latency_rings_host(self._h, rq.ctypes.data, rb.ctypes.data))
+        return rq, rb
+
     def set_dynamics_rand(self, rand=None):
         """Randomizer values [n][12] (`rand_params` layout) for the next mass_matrix / inverse_dynamics /
         forward_dynamics calls; None restores the model's own parameters."""

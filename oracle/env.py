@@ -34,7 +34,8 @@ DEFAULT_TASK = dict(
 BUTTER_B = np.array([0.10669309218914798, 0.21338618437829596, 0.10669309218914798])
 BUTTER_A = np.array([1.0, -0.8877194537361395, 0.31449182249273155])
 
-HIST = 4          # ring entries kept (latency 2 substeps needs entries 0..3, minitaur.py:336-357)
+HIST = 44         # ring entries kept: latency <= 0.04 s = 40 substeps needs entries 0..41 (minitaur.py:336-357; the
+                  # reference keeps 100)
 TRUE_OBS = 43     # minitaur.py:304-311
 
 
@@ -108,7 +109,7 @@ class OracleEnv(object):
         self.inertia_scale = np.ones((N, nb))
         self.foot_friction = np.full(N, -1.0)            # < 0: the URDF value
         self.joint_friction = np.zeros((N, 12))          # Coulomb torque limit per URDF joint coordinate
-        self.ctrl_latency = np.zeros(N)                  # sampled, NOT applied (DESIGN.md "out of scope")
+        self.ctrl_latency = np.full(N, float(s.ctrl_latency))   # set_ctrl_latency (minitaur.py:377-385)
         self.rand_values = None
         self.default_pose = np.concatenate([s.init_pos, s.init_quat,
                                             (s.init_motor + s.joint_offset) * s.joint_dir])  # minitaur.py:1190-1194
@@ -130,18 +131,19 @@ class OracleEnv(object):
         return np.concatenate([self.motor_angles_true(), self.motor_vels_true(), self.obs_torque, rel, w_local], axis=-1)
 
     def _delay_obs(self, latency):
+        """minitaur.py:336-357 with a per-robot latency (the randomizer sets it, :377-385)."""
         dt = self.spec.time_step
+        latency = np.broadcast_to(np.asarray(latency, dtype=np.float64), (self.N,))
         newest = self.hist[:, 0]
-        if latency <= 0:
-            return newest.copy()
-        n = int(latency / dt)
-        assert n + 1 < HIST
+        n = (latency / dt).astype(np.int64)                      # int(latency / self.time_step)
+        assert np.all(n + 1 < HIST)
         rem = latency - n * dt
-        alpha = rem / dt
-        blend = (1.0 - alpha) * self.hist[:, n] + alpha * self.hist[:, n + 1]
-        oldest = self.hist[np.arange(self.N), np.clip(self.hist_len - 1, 0, HIST - 1)]
+        alpha = (rem / dt)[:, None]
+        r = np.arange(self.N)
+        blend = (1.0 - alpha) * self.hist[r, n] + alpha * self.hist[r, n + 1]
+        oldest = self.hist[r, np.clip(self.hist_len - 1, 0, HIST - 1)]
         out = np.where((n + 1 >= self.hist_len)[:, None], oldest, blend)
-        return np.where((self.hist_len == 1)[:, None], newest, out)
+        return np.where(((self.hist_len == 1) | (latency <= 0))[:, None], newest, out)
 
     def receive_obs(self, mask=None):
         """minitaur.py:313-334."""
@@ -150,7 +152,7 @@ class OracleEnv(object):
         shifted = np.concatenate([new[:, None], self.hist[:, :-1]], axis=1)
         self.hist = np.where(m[:, None, None], shifted, self.hist)
         self.hist_len = np.where(m, np.minimum(self.hist_len + 1, 100), self.hist_len)
-        self.ctrl_obs = np.where(m[:, None], self._delay_obs(self.spec.ctrl_latency), self.ctrl_obs)
+        self.ctrl_obs = np.where(m[:, None], self._delay_obs(self.ctrl_latency), self.ctrl_obs)
 
     def get_motor_angles(self):
         return xf.MapToMinusPiToPi(self.ctrl_obs[:, 0:12])           # minitaur.py:555-567

@@ -75,7 +75,6 @@ def load_rand_params(oracle, rp):
         rm[:, i + 1] = rp[:, 1]; ri[:, i + 1] = rp[:, 3]
     oracle.link_mass = rm * np.asarray(t.mass, dtype=np.float64)[None, :]
     oracle.inertia_scale = ri
-    oracle.ctrl_latency = rp[:, 4].copy()
     oracle.foot_friction = np.where(rp[:, 5] >= 0, rp[:, 5] / oracle.phys["mu_plane"], -1.0)
     jf = np.zeros((N, 12))
     knees = [i for i in ids["foot"] if t.movable[i]]               # one per leg, URDF leg order
@@ -84,7 +83,7 @@ def load_rand_params(oracle, rp):
     oracle.joint_friction = jf
 
 
-def sync_oracle_from_product(oracle, st):
+def sync_oracle_from_product(oracle, st, rings=None):
     """Load a product state dict (BatchedImitationEnv.get_state) into an OracleEnv (float32 values widened)."""
     f = lambda a: np.asarray(a, dtype=np.float64)
     oracle.pos, oracle.quat, oracle.q = f(st["pos"]), f(st["quat"]), f(st["q"])
@@ -109,15 +108,33 @@ def sync_oracle_from_product(oracle, st):
         load_rand_params(oracle, f(st["rand_params"]))
     # observation ring: entry 0 = current true state, entries 1/2 carry the delayed motor angles
     N = oracle.N
-    oracle.hist = np.zeros((N, 4, 43))
-    oracle.hist_len = np.full(N, 4, dtype=np.int64)
-    oracle.hist[:, 0] = oracle._true_obs()
-    oracle.hist[:, 1, 0:12] = f(st["ring1"])
-    oracle.hist[:, 2, 0:12] = f(st["ring2"])
-    oracle.hist[:, 1, 36:40] = [0, 0, 0, 1]
-    oracle.hist[:, 2, 36:40] = f(st["obs_quat"])
-    oracle.hist[:, 3] = oracle.hist[:, 2]
-    oracle.ctrl_obs = oracle.hist[:, 2].copy()
+    from oracle.env import HIST
+    oracle.hist = np.zeros((N, HIST, 43))
+    if rings is None:
+        oracle.hist_len = np.full(N, 4, dtype=np.int64)
+        oracle.hist[:, 0] = oracle._true_obs()
+        oracle.hist[:, 1, 0:12] = f(st["ring1"])
+        oracle.hist[:, 2, 0:12] = f(st["ring2"])
+        oracle.hist[:, 1, 36:40] = [0, 0, 0, 1]
+        oracle.hist[:, 2, 36:40] = f(st["obs_quat"])
+        oracle.hist[:, 3] = oracle.hist[:, 2]
+        oracle.ctrl_obs = oracle.hist[:, 2].copy()
+    else:
+        # randomised control latency: rebuild the observation history from the product's rings
+        # (entry E in slot E % 42, newest entry = substep counter + 1)
+        ring_q, ring_b = rings
+        R = ring_q.shape[1]
+        oracle.ctrl_latency = f(st["rand_params"][:, 4])
+        el = st["substep_counter"].astype(np.int64) + 1
+        oracle.hist_len = np.minimum(el + 1, HIST)
+        r = np.arange(N)
+        for h in range(HIST):
+            e = np.maximum(el - h, 0)
+            oracle.hist[:, h, 0:12] = ring_q[r, e % R]
+            oracle.hist[:, h, 36:40] = ring_b[r, e % R, 0:4]
+            oracle.hist[:, h, 40:43] = ring_b[r, e % R, 4:7]
+        oracle.hist[:, 0] = oracle._true_obs()            # the newest entry is the current true state (float64 of the same values)
+        oracle.ctrl_obs = oracle._delay_obs(oracle.ctrl_latency)
 
 
 def rel_err(a, b, floor=1e-12):

@@ -330,7 +330,7 @@ def test_randomized_control_step_matches_oracle():
     env.reset(); orc.reset()
     rng = np.random.default_rng(2)
     for step in range(3):
-        common.sync_oracle_from_product(orc, env.get_state())
+        common.sync_oracle_from_product(orc, env.get_state(), rings=env.latency_rings())
         act = rng.normal(scale=0.2, size=(N, 12)).astype(np.float32)
         o, r, d = env.step(torch.as_tensor(act, device=env.device))
         oo, ro, do = orc.step(act.astype(np.float64))
@@ -340,6 +340,7 @@ def test_randomized_control_step_matches_oracle():
         assert ok.mean() > 0.95
         assert np.abs(r - ro)[ok].max() <= 1e-4 and np.median(np.abs(r - ro)) <= 5e-6
         assert np.abs(st["q"] - orc.q)[ok].max() <= 2e-4 and np.abs(st["pos"] - orc.pos)[ok].max() <= 1e-4
+        assert np.abs(o - oo)[ok].max() <= 2e-2 and np.median(np.abs(o - oo)) <= 1e-5     # incl. the delayed sensor readings
     # the randomised robots really move differently from the nominal ones
     nominal = common.make_product("laikago", ["laikago_pace"], N, seed=5)
     nominal.reset()
@@ -350,6 +351,42 @@ def test_randomized_control_step_matches_oracle():
     nominal.step(z); env.step(z)
     assert np.abs(nominal.get_state()["q"] - env.get_state()["q"]).max() > 1e-3
     env.close(); nominal.close()
+
+
+@pytest.mark.parametrize("latency", [0.0, 0.0003, 0.001, 0.002, 0.0137, 0.04])
+def test_randomised_control_latency_matches_oracle(latency):
+    """_get_delay_obs (minitaur.py:336-357) with the latency the randomizer sets: 0, a fraction of a substep, whole
+    substeps, the default, 13.7 substeps, and the maximum (40 substeps: longer than one control step, and longer than
+    the history right after a reset, where the oldest entry is returned)."""
+    N = 64
+    env = common.make_product("laikago", ["laikago_pace"], N, seed=9, randomizer=True)
+    orc = common.make_oracle("laikago", ["laikago_pace"], N, seed=9, randomizer=True)
+    env.reset(); orc.reset()
+    st = env.get_state()
+    rp = st["rand_params"].copy(); rp[:, 4] = latency
+    env.set_state(dict(rand_params=rp))
+    # the control observation of the FIRST step was fixed at reset with the sampled latency: redo it for the forced one
+    rq, rb = env.latency_rings()
+    n, al = int(np.float32(latency) / 1e-3), np.float32(latency) / 1e-3 - int(np.float32(latency) / 1e-3)
+    first = (1 - al) * rq[:, 1] + al * rq[:, 0] if n == 0 else rq[:, 0]
+    env.set_state(dict(ring2=first.astype(np.float32)))
+    rng = np.random.default_rng(1)
+    for step in range(4):                          # 4 x 33 substeps: the 40-substep latency reaches past a whole step
+        common.sync_oracle_from_product(orc, env.get_state(), rings=env.latency_rings())
+        assert np.allclose(orc.ctrl_latency, np.float32(latency))
+        act = rng.normal(scale=0.1, size=(N, 12)).astype(np.float32)
+        o, r, d = env.step(torch.as_tensor(act, device=env.device))
+        oo, ro, do = orc.step(act.astype(np.float64))
+        o = o.cpu().numpy()
+        st = env.get_state()
+        ok = np.abs(st["qd"] - orc.qd).max(axis=1) < 2e-2
+        assert ok.mean() > 0.9
+        # delayed motor angles and IMU channels of the newest history row, then the whole observation
+        assert np.abs(st["ang_hist"][:, 0] - orc.ang_hist[:, 0])[ok].max() <= 2e-4
+        assert np.abs(st["imu_hist"][:, 0] - orc.imu_hist[:, 0])[ok].max() <= 5e-3
+        assert np.median(np.abs(o - oo)) <= 1e-5
+        assert np.abs(st["q"] - orc.q)[ok].max() <= 2e-4
+    env.close()
 
 
 def test_time_limit_and_termination_thresholds(laikago):
