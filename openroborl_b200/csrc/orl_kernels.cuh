@@ -731,10 +731,23 @@ __global__ void __launch_bounds__(ORL_BLOCK_THREADS, ORL_STEP_MIN_BLOCKS) orl_st
   if (leg == 0) S[S_EPRET] = ep_ret;
   if (valid && leg == 0) { reward_out[robot] = reward; done_out[robot] = (uint8_t)done; }
   __syncwarp();
+#ifdef ORL_PROFILE_RARE
+  const long long tr0 = clock64();
+  const bool any_finish = __any_sync(0xffffffffu, finish);
+#endif
   if (finish) reset_robot(S, E, *Mo, C.gid0 + robot_c, leg, 0xFu << (lane & ~3));
+#ifdef ORL_PROFILE_RARE
+  __syncwarp();
+  if (lane == 0 && any_finish) { atomicAdd(&orl_prof[7], (unsigned long long)(clock64() - tr0)); atomicAdd(&orl_prof[0], 0ull); atomicAdd(&orl_prof[23], 1ull); }
+  const long long to0 = clock64();
+#endif
   __syncwarp();
   // 7. observation (histories + target frames)
   build_obs(S, O, E, leg);
+#ifdef ORL_PROFILE_RARE
+  __syncwarp();
+  if (lane == 0) atomicAdd(&orl_prof[22], (unsigned long long)(clock64() - to0));
+#endif
   stage_out(E, st, ob, obs_out);
 }
 
