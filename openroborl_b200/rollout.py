@@ -68,8 +68,9 @@ class MlpGaussianPolicy(object):
         return torch.addmm(p[head + "/b"], h, p[head + "/w"])
 
     @torch.no_grad()
-    def step(self, obs, deterministic=False, generator=None):
-        """obs [N,160] -> (action [N,12], value [N], neglogp [N]); mirrors ActorCriticPolicy.step."""
+    def step(self, obs, deterministic=False, generator=None, noise=None):
+        """obs [N,160] -> (action [N,12], value [N], neglogp [N]); mirrors ActorCriticPolicy.step.
+        `noise`: pre-drawn standard normal [N,12] (CUDA-graph friendly) instead of drawing from `generator`."""
         prev = torch.backends.cuda.matmul.allow_tf32
         torch.backends.cuda.matmul.allow_tf32 = self.tf32
         try:
@@ -79,6 +80,8 @@ class MlpGaussianPolicy(object):
             torch.backends.cuda.matmul.allow_tf32 = prev
         if deterministic:
             action = mean
+        elif noise is not None:
+            action = mean + self.std * noise
         else:
             action = mean + self.std * torch.randn(mean.shape, device=mean.device, dtype=mean.dtype, generator=generator)
         # DiagGaussianProbabilityDistribution.neglogp
@@ -114,10 +117,16 @@ class RolloutCollector(object):
     robots restart individually inside the step kernel and only their own bootstrap value is cut.
     """
 
-    def __init__(self, env, policy, horizon, gamma=0.95, lam=0.95, reset_all_on_any_done=True, seed=0):
+    def __init__(self, env, policy, horizon, gamma=0.95, lam=0.95, reset_all_on_any_done=True, seed=0, use_cuda_graph=False):
         self.env, self.policy, self.T = env, policy, int(horizon)
         self.gamma, self.lam = gamma, lam
         self.reset_all = reset_all_on_any_done
+        # The T-step loop is ~25 small launches per step (policy GEMMs, elementwise bookkeeping, the env step kernel):
+        # with an auto-reset env nothing in it depends on the host, so it can be captured once and replayed.
+        if use_cuda_graph and reset_all_on_any_done:
+            raise ValueError("use_cuda_graph needs reset_all_on_any_done=False (the reference's reset-all is a host decision)")
+        self.use_graph = bool(use_cuda_graph)
+        self._graph, self._seg = None, None
         N, dev = env.num_robot, env.device
         self.obs_buf = torch.empty((self.T, N, 160), dtype=torch.float32, device=dev)
         self.act_buf = torch.empty((self.T, N, 12), dtype=torch.float32, device=dev)
@@ -131,13 +140,36 @@ class RolloutCollector(object):
         self.low, self.high = -2.0 * math.pi, 2.0 * math.pi            # env.action_space (minitaur.py:145-148)
         self.obs = env.reset().clone()
         self.episode_start = torch.ones(N, dtype=torch.uint8, device=dev)
+        self.noise_buf = torch.empty((self.T, N, 12), dtype=torch.float32, device=dev) if self.use_graph else None
 
     @torch.no_grad()
     def collect(self):
+        if not self.use_graph:
+            return self._collect()
+        if self._graph is None:                      # warm up on a side stream, then capture the whole segment
+            self.noise_buf.normal_(generator=self.gen)
+            side = torch.cuda.Stream(device=self.env.device)
+            side.wait_stream(torch.cuda.current_stream(self.env.device))
+            with torch.cuda.stream(side):
+                self._collect()
+            torch.cuda.current_stream(self.env.device).wait_stream(side)
+            torch.cuda.synchronize(self.env.device)
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                self._seg = self._collect()
+        self.noise_buf.normal_(generator=self.gen)
+        self._graph.replay()
+        return self._seg
+
+    @torch.no_grad()
+    def _collect(self):
         env, pol, T = self.env, self.policy, self.T
         self.nextv_buf.zero_()
         for t in range(T):
-            action, value, _ = pol.step(self.obs, generator=self.gen)
+            if self.use_graph:
+                action, value, _ = pol.step(self.obs, noise=self.noise_buf[t])
+            else:
+                action, value, _ = pol.step(self.obs, generator=self.gen)
             self.obs_buf[t] = self.obs
             self.vpred_buf[t] = value
             self.act_buf[t] = action                                   # the runner stores the UNclipped action (:132)
@@ -149,15 +181,15 @@ class RolloutCollector(object):
             obs, rew, done = env.step(clipped)
             self.rew_buf[t] = rew
             self.done_buf[t] = done
-            self.episode_start = done.clone()
+            self.episode_start.copy_(done)
             if self.reset_all:
                 if bool(done.any()):                                   # :185-205
                     self.nextv_buf[t].zero_()
-                    self.obs = env.reset().clone()
+                    self.obs.copy_(env.reset())
                 else:
-                    self.obs = obs.clone()
+                    self.obs.copy_(obs)
             else:
-                self.obs = obs.clone()
+                self.obs.copy_(obs)
         # segment end: the reference bootstraps the last row with 0.0 (imitation_runners.py:93-97)
         self.nextv_buf[T - 1].zero_()
         adv, ret = gae(self.rew_buf, self.vpred_buf, self.nextv_buf, self.start_buf, self.gamma, self.lam,

@@ -101,3 +101,40 @@ def test_rollout_collector_layout_and_semantics():
     stats = env2.stats()
     assert stats[3] == T * N and stats[2] >= 2 * N
     env.close(); env2.close()
+
+
+def test_rollout_collector_cuda_graph_mode():
+    """The captured T-step segment (policy forward + env step + bookkeeping + GAE) replays with the same semantics."""
+    from openroborl_b200.rollout import MlpGaussianPolicy, RolloutCollector
+    N, T = 96, 8
+    pol = MlpGaussianPolicy(_params(), "cuda")
+    env = common.make_product("laikago", ["laikago_pace"], N, seed=2, auto_reset=True, max_episode_steps=6)
+    with pytest.raises(ValueError):
+        RolloutCollector(env, pol, T, reset_all_on_any_done=True, use_cuda_graph=True)
+    col = RolloutCollector(env, pol, T, reset_all_on_any_done=False, seed=5, use_cuda_graph=True)
+    env.stats(reset=True)
+    segs = []
+    for it in range(3):                                  # capture + two replays
+        seg = col.collect()
+        segs.append({k: (v.clone() if torch.is_tensor(v) else v) for k, v in seg.items()})
+    for seg in segs:
+        vp, nv = seg["vpred"].reshape(T, N), seg["nextvpreds"].reshape(T, N)
+        st, dn = seg["episode_starts"].reshape(T, N).bool(), seg["dones"].reshape(T, N).bool()
+        assert torch.equal(st[1:], dn[:-1]) and torch.equal(nv[T - 1], torch.zeros_like(nv[T - 1]))
+        for t in range(T - 1):
+            keep = ~st[t + 1]
+            assert torch.equal(nv[t][keep], vp[t + 1][keep])
+        assert torch.isfinite(seg["adv"]).all() and torch.isfinite(seg["tdlamret"]).all()
+        # GAE of the captured kernel against the oracle on the segment's own buffers
+        a_ref, r_ref = oppo.add_vtarg_and_adv(seg["rewards"].cpu().numpy(), seg["vpred"].cpu().numpy(), seg["nextvpreds"].cpu().numpy(),
+                                              seg["episode_starts"].cpu().numpy().astype(bool), N, 0.95, 0.95)
+        np.testing.assert_allclose(seg["tdlamret"].cpu().numpy(), r_ref, rtol=1e-4, atol=1e-4)
+    # segments continue each other: every robot hits the 6-step limit in each 8-step segment, noise differs between replays
+    total = sum(seg["dones"].reshape(T, N).sum(dim=0) for seg in segs)
+    assert int(total.min()) >= 3
+    assert not torch.equal(segs[1]["actions"], segs[2]["actions"])
+    assert torch.equal(segs[1]["episode_starts"].reshape(T, N)[0], segs[0]["dones"].reshape(T, N)[T - 1])
+    assert torch.equal(segs[2]["episode_starts"].reshape(T, N)[0], segs[1]["dones"].reshape(T, N)[T - 1])
+    st = env.stats()
+    assert st[3] == 4 * T * N                            # the warm-up pass and the three replays stepped the env; the capture did not
+    env.close()
