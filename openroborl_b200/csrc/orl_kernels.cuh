@@ -543,7 +543,7 @@ __global__ void __launch_bounds__(ORL_BLOCK_THREADS, ORL_STEP_MIN_BLOCKS) orl_st
     orl_prof_warp[0][gw] = 0; orl_prof_warp[1][gw] = 0;
     int b = (int)(rc / 8192); if (b > 7) b = 7;
     atomicAdd(&orl_prof[8 + b], 1ull);                    // histogram of rare cycles per warp-step, 8k-cycle buckets
-    int t = (int)(rt / 16); if (t > 7) t = 7;
+    int t = (int)(rt / 16); if (t > 3) t = 3;
     atomicAdd(&orl_prof[16 + t], 1ull);                   // histogram of rare trips per warp-step, buckets of 16
     atomicMax(&orl_prof[5], rc); atomicMax(&orl_prof[6], rt);
   }
