@@ -43,9 +43,9 @@ struct DevEnv {
 };
 // ORL_LAT_RING (orl.h) = 42: latency <= 0.04 s = 40 substeps, entries E-41 .. E are live
 
-// Thread block = ORL_WARPS_PER_BLOCK warps that run the substep loop in lockstep (one barrier per substep): the loop
-// body (~33 KB of SASS) is larger than the SM's 32 KB instruction cache, and warps of one block that stay within the
-// same code region share every fetched line instead of thrashing the cache at four different positions.
+// Thread block = ORL_WARPS_PER_BLOCK independent warps sharing one copy of the packed model in shared memory.
+// (Running them in lockstep with a barrier per substep, so that they would share fetched instruction lines, was
+// measured and brought nothing: profiles/r01_v4_step_kernel.md; -DORL_LOCKSTEP re-enables it.)
 #ifndef ORL_WARPS_PER_BLOCK
 #define ORL_WARPS_PER_BLOCK 4
 #endif
@@ -329,6 +329,7 @@ struct LaneDyn {
 struct LaneCtl {
   float target[3], prevf[3];
   float strength[3];
+  float4 c1[3], m0[3], m1[3];   // joint limits / motor constants of this lane's joints (registers are not scarce since the ABA rewrite)
   float fric[3];             // Coulomb friction torque of this lane's joints (randomizer; 0: none)
   RandLane rl;
   int lat_n; float lat_a;    // control latency = (lat_n + lat_a) substeps (LAT kernels)
@@ -374,7 +375,7 @@ ORL_DI void substep(const DevLeg& L, const DevModel& Mo, const PhysParams& P, co
   float tau[3], qm_now[3];
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
-    const float4 c1 = L.j[k].c1, m0 = L.j[k].m0, m1 = L.j[k].m1;   // (comy comz lower upper) (damping dir offset kp) (kd init motor brad)
+    const float4 c1 = Ctl.c1[k], m0 = Ctl.m0[k], m1 = Ctl.m1[k];   // (comy comz lower upper) (damping dir offset kp) (kd init motor brad)
     const float strength = Ctl.strength[k];
     const float qm = (D.q[k] - m0.z) * m0.y;                               // :549-553
     float ctrl = D.r2[k];
@@ -498,6 +499,7 @@ __global__ void __launch_bounds__(ORL_BLOCK_THREADS, ORL_STEP_MIN_BLOCKS) orl_st
   for (int k = 0; k < 3; ++k) {
     Ctl.target[k] = target[k]; Ctl.prevf[k] = prevf[k]; Ctl.strength[k] = S[S_STRENGTH + __float_as_int(L.j[k].m1.z)];
     Ctl.fric[k] = __float_as_int(L.j[k].i3.w) >= 0 ? S[S_RAND + 6 + leg] : 0.f;
+    Ctl.c1[k] = L.j[k].c1; Ctl.m0[k] = L.j[k].m0; Ctl.m1[k] = L.j[k].m1;
   }
   Ctl.rl.base_mass_ratio = S[S_RAND + 0]; Ctl.rl.base_inertia_ratio = S[S_RAND + 2]; Ctl.rl.mu_foot = S[S_RAND + 5];
   {
@@ -530,8 +532,8 @@ __global__ void __launch_bounds__(ORL_BLOCK_THREADS, ORL_STEP_MIN_BLOCKS) orl_st
   const long long tl0 = clock64();
 #endif
   for (int s = 0; s < AR; ++s) {
-#if ORL_WARPS_PER_BLOCK > 1 && !defined(ORL_NO_LOCKSTEP)
-    __syncthreads();                       // keep the block's warps in the same code region (shared I-cache lines)
+#if ORL_WARPS_PER_BLOCK > 1 && defined(ORL_LOCKSTEP)
+    __syncthreads();                       // experiment: keep the block's warps in the same code region (no gain measured)
 #endif
     substep<LAT>(L, *Mo, P, Ctl, D, S, X, s);
   }
