@@ -502,7 +502,7 @@ __global__ void __launch_bounds__(ORL_BLOCK_THREADS, ORL_STEP_MIN_BLOCKS) orl_st
     Ctl.c1[k] = L.j[k].c1; Ctl.m0[k] = L.j[k].m0; Ctl.m1[k] = L.j[k].m1;
   }
   Ctl.rl.base_mass_ratio = S[S_RAND + 0]; Ctl.rl.base_inertia_ratio = S[S_RAND + 2]; Ctl.rl.mu_foot = S[S_RAND + 5];
-  rand_lane_toe(L, Ctl.rl);
+  rand_lane_toe(L, *Mo, Ctl.rl);
   {
     const float ratios[4] = {S[S_RAND + 0], S[S_RAND + 1], S[S_RAND + 2], S[S_RAND + 3]};
     fill_scaled_inertia(L, ratios, X + ORL_XI_BASE * ORL_X_STRIDE);
@@ -842,7 +842,7 @@ __global__ void orl_dyn_kernel(const DevModel* Mo, PhysParams P, int mode, const
   float4* X = Xs + (threadIdx.x >> 5) * (ORL_X_FLOAT4_PER_LANE * ORL_X_STRIDE) + (threadIdx.x & 31);
   RandLane RL; RL.base_mass_ratio = rand ? rand[(size_t)i * 12 + 0] : 1.f; RL.base_inertia_ratio = rand ? rand[(size_t)i * 12 + 2] : 1.f;
   RL.mu_foot = rand ? rand[(size_t)i * 12 + 5] : -1.f;
-  rand_lane_toe(L, RL);
+  rand_lane_toe(L, *Mo, RL);
   {
     const float ratios[4] = {RL.base_mass_ratio, rand ? rand[(size_t)i * 12 + 1] : 1.f, RL.base_inertia_ratio, rand ? rand[(size_t)i * 12 + 3] : 1.f};
     fill_scaled_inertia(L, ratios, X + ORL_XI_BASE * ORL_X_STRIDE);
