@@ -329,6 +329,7 @@ extern "C" int orl_load_motions(orl_env* e, const double* frames, const int32_t*
                                 const int32_t* flags, int32_t n_clips) {
   if (!e) return ORL_ERR_INVALID;
   if (n_clips <= 0) return fail(e, ORL_ERR_INVALID, "No reference motions specified.");   // imitation_task.py:583-584
+  if (n_clips > ORL_MAX_CLIPS) return fail(e, ORL_ERR_INVALID, "at most %d motion clips per environment (%d given)", ORL_MAX_CLIPS, n_clips);
   if (!frames || !n_frames || !frame_dur || !flags) return fail(e, ORL_ERR_INVALID, "null argument");
   CUDA_TRY(e, cudaSetDevice(e->device));
   free_motions(e);
@@ -429,13 +430,11 @@ extern "C" int orl_load_motions(orl_env* e, const double* frames, const int32_t*
   int rc;
   if ((rc = upload(e, f32, &T.frames))) return rc;
   if ((rc = upload(e, v32, &T.vels))) return rc;
-  if ((rc = upload(e, h_start, &T.start))) return rc;
-  if ((rc = upload(e, h_nf, &T.nframes))) return rc;
-  if ((rc = upload(e, h_flags, &T.flags))) return rc;
-  if ((rc = upload(e, h_fd, &T.fd))) return rc;
-  if ((rc = upload(e, e->h_dur, &T.dur))) return rc;
-  if ((rc = upload(e, e->h_dheading, &T.dheading))) return rc;
-  if ((rc = upload(e, h_dposf, &T.dpos))) return rc;
+  for (int c = 0; c < n_clips; ++c) {
+    T.start[c] = h_start[c]; T.nframes[c] = h_nf[c]; T.flags[c] = h_flags[c];
+    T.fd[c] = h_fd[c]; T.dur[c] = e->h_dur[c]; T.dheading[c] = e->h_dheading[c];
+    for (int k = 0; k < 3; ++k) T.dpos[c * 3 + k] = h_dposf[c * 3 + k];
+  }
   if ((rc = upload(e, h_cyc, &T.cyc_table))) return rc;
   if ((rc = upload(e, h_warm, &T.warm_pose))) return rc;
   T.n_clips = n_clips;

@@ -10,16 +10,19 @@
 
 #define ORL_FRAME_STRIDE 20   // 19 (pose) / 18 (vel) floats padded to 20
 
+#define ORL_MAX_CLIPS 32
 struct MotionTables {
   const float* frames;        // [sumF][20] post-processed poses
   const float* vels;          // [sumF][20] frame velocities
-  const int32_t* start;       // first row of clip c
-  const int32_t* nframes;
-  const int32_t* flags;       // bit0 wrap, bit1 cycle pos, bit2 cycle rot
-  const double* fd;           // frame duration
-  const double* dur;          // fd * (F - 1), computed on the host in double like motion_data.py:205-207
-  const double* dheading;     // cycle delta heading
-  const float* dpos;          // [c][3] cycle delta pos
+  // Per-clip scalars travel with the kernel parameters (constant bank): every motion function starts from them, and a
+  // round trip to L2 for five scalars was the first of three dependent memory latencies of each reference sample.
+  double fd[ORL_MAX_CLIPS];        // frame duration
+  double dur[ORL_MAX_CLIPS];       // fd * (F - 1), computed on the host in double like motion_data.py:205-207
+  double dheading[ORL_MAX_CLIPS];  // cycle delta heading
+  int32_t start[ORL_MAX_CLIPS];    // first row of clip c
+  int32_t nframes[ORL_MAX_CLIPS];
+  int32_t flags[ORL_MAX_CLIPS];    // bit0 wrap, bit1 cycle pos, bit2 cycle rot
+  float dpos[ORL_MAX_CLIPS * 3];   // [c][3] cycle delta pos
   const float* cyc_table;     // [c][ORL_CYCLE_TABLE][3] pre-summed rotating cycle offsets (motion_data.py:607-613)
   const float* warm_pose;     // [c][20] warm-up pose (imitation_task.py:985-1009)
   int32_t n_clips;
