@@ -632,6 +632,8 @@ extern "C" int orl_stats(orl_env* e, double out[4], int32_t reset_after) {
     fprintf(stderr, "[orl rare] cycles hist (8k buckets):"); for (int i = 0; i < 8; ++i) fprintf(stderr, " %llu", h[8 + i]);
     fprintf(stderr, "\n[orl rare] trips hist (16 buckets):"); for (int i = 0; i < 4; ++i) fprintf(stderr, " %llu", h[16 + i]);
     fprintf(stderr, "\n[orl rare] backward pass without rare contacts: %.0f cycles (n=%llu); with: %.0f cycles", h[20] ? (double)h[21] / (double)h[20] : 0.0, h[20], h[0] ? (double)h[2] / (double)h[0] : 0.0);
+    fprintf(stderr, "\n[orl rare] per warp-step cycles: stage_in %.0f | prologue %.0f | loop %.0f | epilogue (loop end -> stage_out) %.0f | stage_out %.0f", (double)h[12] / h[4], (double)h[13] / h[4], (double)h[3] / h[4], (double)h[15] / h[4], (double)h[14] / h[4]);
+    fprintf(stderr, "\n[orl rare] epilogue sections per warp-step: writeback+sensors %.0f | reward %.0f | reference update %.0f | termination %.0f", (double)h[8] / h[4], (double)h[9] / h[4], (double)h[10] / h[4], (double)h[11] / h[4]);
     fprintf(stderr, "\n[orl rare] reset path: %llu warp-steps with a reset, %.0f cycles each | build_obs %.0f cycles per warp-step\n", h[23],
             h[23] ? (double)h[7] / (double)h[23] : 0.0, h[4] ? (double)h[22] / (double)h[4] : 0.0);
     unsigned long long z[24] = {0}; cudaMemcpyToSymbol(orl_prof, z, sizeof(z)); }

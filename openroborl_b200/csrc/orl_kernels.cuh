@@ -450,9 +450,15 @@ ORL_DI void substep(const DevLeg& L, const DevModel& Mo, const PhysParams& P, co
 template <bool LAT>
 __global__ void __launch_bounds__(ORL_BLOCK_THREADS, ORL_STEP_MIN_BLOCKS) orl_step_kernel(DevEnv E, const float* __restrict__ actions, float* __restrict__ obs_out,
                                                       float* __restrict__ reward_out, uint8_t* __restrict__ done_out) {
+#ifdef ORL_PROFILE_RARE
+  const long long tk0 = clock64();
+#endif
   extern __shared__ __align__(16) unsigned char smem[];
   const DevModel* Mo; float* st; float* ob;
   stage_in(E, smem, Mo, st, ob);
+#ifdef ORL_PROFILE_RARE
+  const long long tk1 = clock64();
+#endif
   const DevCfg& C = E.cfg;
   const int lane = threadIdx.x & 31, leg = lane & 3, rw = lane >> 2;
   const int robot = warp_row0() + rw;
@@ -531,6 +537,7 @@ __global__ void __launch_bounds__(ORL_BLOCK_THREADS, ORL_STEP_MIN_BLOCKS) orl_st
   __syncwarp();
 #ifdef ORL_PROFILE_RARE
   const long long tl0 = clock64();
+  if ((threadIdx.x & 31) == 0) { atomicAdd(&orl_prof[12], (unsigned long long)(tk1 - tk0)); atomicAdd(&orl_prof[13], (unsigned long long)(tl0 - tk1)); }
 #endif
   for (int s = 0; s < AR; ++s) {
 #if ORL_WARPS_PER_BLOCK > 1 && defined(ORL_LOCKSTEP)
@@ -539,13 +546,14 @@ __global__ void __launch_bounds__(ORL_BLOCK_THREADS, ORL_STEP_MIN_BLOCKS) orl_st
     substep<LAT>(L, *Mo, P, Ctl, D, S, X, s);
   }
 #ifdef ORL_PROFILE_RARE
+  const long long tend_loop = clock64();
   if (lane == 0) {
     atomicAdd(&orl_prof[3], (unsigned long long)(clock64() - tl0)); atomicAdd(&orl_prof[4], 1ull);
     const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const unsigned long long rc = orl_prof_warp[0][gw], rt = orl_prof_warp[1][gw];
     orl_prof_warp[0][gw] = 0; orl_prof_warp[1][gw] = 0;
     int b = (int)(rc / 8192); if (b > 7) b = 7;
-    atomicAdd(&orl_prof[8 + b], 1ull);                    // histogram of rare cycles per warp-step, 8k-cycle buckets
+    (void)b;
     int t = (int)(rt / 16); if (t > 3) t = 3;
     atomicAdd(&orl_prof[16 + t], 1ull);                   // histogram of rare trips per warp-step, buckets of 16
     atomicMax(&orl_prof[5], rc); atomicMax(&orl_prof[6], rt);
@@ -609,6 +617,9 @@ __global__ void __launch_bounds__(ORL_BLOCK_THREADS, ORL_STEP_MIN_BLOCKS) orl_st
     for (int i = 11; i >= 4; --i) S[S_IMU + i] = S[S_IMU + i - 4];
     S[S_IMU + 0] = roll; S[S_IMU + 1] = pitch; S[S_IMU + 2] = obs_w.x; S[S_IMU + 3] = obs_w.y;
   }
+#ifdef ORL_PROFILE_RARE
+  long long tsec = clock64(); if (lane == 0) atomicAdd(&orl_prof[8], (unsigned long long)(tsec - tend_loop));
+#endif
   // 4. reward against the reference state of the END of the previous step (imitation_task.py:341-516)
   const M3 Rb = qmat(quat);
   LegFK Ks, Kr;
@@ -658,6 +669,9 @@ __global__ void __launch_bounds__(ORL_BLOCK_THREADS, ORL_STEP_MIN_BLOCKS) orl_st
   const int broken = quad_or(!(fabsf(chk) < 3.0e38f) ? 1 : 0);
   if (broken) reward = 0.f;
   __syncwarp();
+#ifdef ORL_PROFILE_RARE
+  { const long long tn = clock64(); if (lane == 0) atomicAdd(&orl_prof[9], (unsigned long long)(tn - tsec)); tsec = tn; }
+#endif
   // 5. task.update (imitation_task.py:201-207, 734-761, 1020-1055)
   RefFrame F = load_ref_frame(S, C);
   const double time = motion_time(S, C);
@@ -682,6 +696,9 @@ __global__ void __launch_bounds__(ORL_BLOCK_THREADS, ORL_STEP_MIN_BLOCKS) orl_st
     S[S_REFPOSE + 7 + 3 * leg + k] = ref_joint(E.mt, F, smp, 3 * leg + k);
     S[S_REFVEL + 6 + 3 * leg + k] = ref_joint_vel(E.mt, F, smp, 3 * leg + k);
   }
+#ifdef ORL_PROFILE_RARE
+  { const long long tn = clock64(); if (lane == 0) atomicAdd(&orl_prof[10], (unsigned long long)(tn - tsec)); tsec = tn; }
+#endif
   // 6. termination against the freshly updated reference (imitation_task.py:518-572, wrapper_env.py:78-80)
   int fall = 0;
   {
@@ -714,6 +731,9 @@ __global__ void __launch_bounds__(ORL_BLOCK_THREADS, ORL_STEP_MIN_BLOCKS) orl_st
     done |= (envstep1 >= C.max_episode_steps) || broken;
   }
   __syncwarp();
+#ifdef ORL_PROFILE_RARE
+  { const long long tn = clock64(); if (lane == 0) atomicAdd(&orl_prof[11], (unsigned long long)(tn - tsec)); tsec = tn; }
+#endif
   // rollout statistics (SURVEY.md section 5 "metrics"): [sum reward, sum episode length, episodes, robot steps]
   float ep_ret = S[S_EPRET] + reward;
   const bool finish = done && C.auto_reset;
@@ -750,8 +770,12 @@ __global__ void __launch_bounds__(ORL_BLOCK_THREADS, ORL_STEP_MIN_BLOCKS) orl_st
 #ifdef ORL_PROFILE_RARE
   __syncwarp();
   if (lane == 0) atomicAdd(&orl_prof[22], (unsigned long long)(clock64() - to0));
+  const long long ts0 = clock64();
 #endif
   stage_out(E, st, ob, obs_out);
+#ifdef ORL_PROFILE_RARE
+  if (lane == 0) { atomicAdd(&orl_prof[14], (unsigned long long)(clock64() - ts0)); atomicAdd(&orl_prof[15], (unsigned long long)(ts0 - tend_loop)); }
+#endif
 }
 
 // =================================================================================================
