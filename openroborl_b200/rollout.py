@@ -154,6 +154,7 @@ class RolloutCollector(object):
                 self._collect()
             torch.cuda.current_stream(self.env.device).wait_stream(side)
             torch.cuda.synchronize(self.env.device)
+            self.env.stats(reset=True)               # the warm-up pass stepped the env; its episodes are not part of a segment
             self._graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self._graph):
                 self._seg = self._collect()
