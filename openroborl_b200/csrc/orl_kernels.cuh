@@ -333,6 +333,7 @@ struct LaneCtl {
   float fric[3];             // Coulomb friction torque of this lane's joints (randomizer; 0: none)
   RandLane rl;
   int lat_n; float lat_a;    // control latency = (lat_n + lat_a) substeps (LAT kernels)
+  int ar;                    // substeps per control step
   int el0;                   // index of the newest observation entry at the first substep of this step (LAT kernels)
   float* ring_q; float* ring_b;   // this robot's rings (LAT kernels)
   float mac, inv_ar;
@@ -364,7 +365,10 @@ ORL_DI void substep(const DevLeg& L, const DevModel& Mo, const PhysParams& P, co
   const int el = Ctl.el0 + s;                                         // LAT: the current true state is observation entry el
   if (LAT) {
     asm volatile("cp.async.wait_all;" ::: "memory");                  // prefetched history entries of this substep
-    if ((threadIdx.x & 3) == 0) {
+    // base part of the observation: only the entries an IMU reading will blend are stored -- history[n], history[n+1]
+    // counted back from the last entry of this control step (el0 + AR) or of the next one (el0 + 2 AR)
+    const int back = Ctl.el0 + Ctl.ar - el - Ctl.lat_n;
+    if ((threadIdx.x & 3) == 0 && (back == 0 || back == 1 || back == -Ctl.ar || back == 1 - Ctl.ar)) {
       Q4 oq; float3 ow;
       obs_base(D, Mo, oq, ow);
       float4* rb = reinterpret_cast<float4*>(Ctl.ring_b + (el % ORL_LAT_RING) * 8);
@@ -516,7 +520,7 @@ __global__ void __launch_bounds__(ORL_BLOCK_THREADS, ORL_STEP_MIN_BLOCKS) orl_st
   Ctl.first_step = first_step; Ctl.mac = Mo->b1.w;
   const int AR = C.action_repeat;
   Ctl.inv_ar = 1.0f / (float)AR; Ctl.capture = AR - 3;
-  Ctl.lat_n = 0; Ctl.lat_a = 0.f; Ctl.el0 = substep0 + 1; Ctl.ring_q = nullptr; Ctl.ring_b = nullptr;
+  Ctl.lat_n = 0; Ctl.lat_a = 0.f; Ctl.el0 = substep0 + 1; Ctl.ring_q = nullptr; Ctl.ring_b = nullptr; Ctl.ar = AR;
   if (LAT) {
     // entries: 0 = default pose (Minitaur.reset), 1 = synced pose (ImitationTask.reset), 2 + j = after substep j
     const double lat = (double)S[S_RAND + 4] / C.sim_dt;
