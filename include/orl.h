@@ -222,6 +222,7 @@ int orl_fk(orl_env* env, const float* pose_dev, int32_t n, float* com_dev, void*
  * angular velocity (3), pad); entry E of a robot sits in slot E % ORL_LAT_RING, E = substep counter + 1.  Either may be NULL. */
 #define ORL_LAT_RING 42
 int orl_get_latency_rings_host(orl_env* env, float* ring_q, float* ring_b);
+int orl_set_latency_rings_host(orl_env* env, const float* ring_q, const float* ring_b);
 /* Randomizer values [n][12] (layout of orl_state_layout.rand_params) used by the three dynamics entry points below;
  * NULL (default) = the model's own masses, inertias and friction. */
 int orl_set_dynamics_rand(orl_env* env, const float* rand_dev);

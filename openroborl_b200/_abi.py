@@ -98,6 +98,7 @@ SYMBOLS = {
     "orl_motion_lookup": (C.c_int, [_P, _P, _P, C.c_int32, _P, _P, _P, _P, _P, _P, _P]),
     "orl_fk": (C.c_int, [_P, _P, C.c_int32, _P, _P]),
     "orl_get_latency_rings_host": (C.c_int, [_P, _P, _P]),
+    "orl_set_latency_rings_host": (C.c_int, [_P, _P, _P]),
     "orl_set_dynamics_rand": (C.c_int, [_P, _P]),
     "orl_mass_matrix": (C.c_int, [_P, _P, C.c_int32, _P, _P]),
     "orl_inverse_dynamics": (C.c_int, [_P, _P, _P, _P, C.c_int32, _P, _P]),

@@ -676,6 +676,16 @@ extern "C" int orl_get_latency_rings_host(orl_env* e, float* ring_q, float* ring
   if (ring_b) CUDA_TRY(e, cudaMemcpy(ring_b, e->dev.ring_b, n * 8 * sizeof(float), cudaMemcpyDeviceToHost));
   return ORL_OK;
 }
+extern "C" int orl_set_latency_rings_host(orl_env* e, const float* ring_q, const float* ring_b) {
+  if (!e) return ORL_ERR_INVALID;
+  if (!e->dev.ring_q) return fail(e, ORL_ERR_INVALID, "the observation rings only exist when the randomizer is enabled");
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  CUDA_TRY(e, cudaDeviceSynchronize());
+  const size_t n = (size_t)e->cfg.num_robot * ORL_LAT_RING;
+  if (ring_q) CUDA_TRY(e, cudaMemcpy(e->dev.ring_q, ring_q, n * 12 * sizeof(float), cudaMemcpyHostToDevice));
+  if (ring_b) CUDA_TRY(e, cudaMemcpy(e->dev.ring_b, ring_b, n * 8 * sizeof(float), cudaMemcpyHostToDevice));
+  return ORL_OK;
+}
 extern "C" int orl_set_dynamics_rand(orl_env* e, const float* rand_dev) {
   if (!e) return ORL_ERR_INVALID;
   e->parity_rand = rand_dev;

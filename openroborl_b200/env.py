@@ -295,6 +295,25 @@ class BatchedImitationEnv(object):
         self._check(self._lib.orl_get_latency_rings_host(self._h, rq.ctypes.data, rb.ctypes.data))
         return rq, rb
 
+    def set_latency_rings(self, ring_q, ring_b):
+        rq = np.ascontiguousarray(ring_q, dtype=np.float32); rb = np.ascontiguousarray(ring_b, dtype=np.float32)
+        if rq.shape != (self.num_robot, 42, 12) or rb.shape != (self.num_robot, 42, 8):
+            raise ValueError("ring shapes must be (N, 42, 12) and (N, 42, 8)")
+        self._check(self._lib.orl_set_latency_rings_host(self._h, rq.ctypes.data, rb.ctypes.data))
+
+    def checkpoint(self):
+        """Everything needed to resume bit-exactly (SURVEY.md section 5 "checkpoint / resume"): the state records and, in
+        randomizer mode, the observation history of the randomised control latency."""
+        ck = dict(state=self.get_state())
+        if self.enable_randomizer:
+            ck["latency_rings"] = self.latency_rings()
+        return ck
+
+    def restore(self, ck):
+        self.set_state(ck["state"])
+        if self.enable_randomizer:
+            self.set_latency_rings(*ck["latency_rings"])
+
     def set_dynamics_rand(self, rand=None):
         """Randomizer values [n][12] (`rand_params` layout) for the next mass_matrix / inverse_dynamics /
         forward_dynamics calls; None restores the model's own parameters."""

@@ -389,6 +389,37 @@ def test_randomised_control_latency_matches_oracle(latency):
     env.close()
 
 
+@pytest.mark.parametrize("rand", [False, True])
+def test_checkpoint_restore_is_bit_exact_and_results_do_not_depend_on_sharding(rand):
+    N = 48
+    acts = [torch.as_tensor(np.random.default_rng(i).normal(scale=0.15, size=(N, 12)).astype(np.float32), device="cuda") for i in range(6)]
+    a = common.make_product("laikago", ["laikago_pace"], N, seed=21, auto_reset=True, randomizer=rand, max_episode_steps=4)
+    a.reset()
+    for i in range(3):
+        a.step(acts[i])
+    ck = a.checkpoint()
+    want = [tuple(x.cpu().numpy().copy() for x in a.step(acts[i])) for i in range(3, 6)]
+    b = common.make_product("laikago", ["laikago_pace"], N, seed=21, auto_reset=True, randomizer=rand, max_episode_steps=4)
+    b.reset()
+    b.restore(ck)
+    for i, w in zip(range(3, 6), want):
+        got = b.step(acts[i])
+        for x, y in zip(got, w):
+            assert np.array_equal(x.cpu().numpy(), y)
+    # two shards keyed by global robot ids reproduce the unsharded batch (incl. the randomizer draws and in-kernel resets)
+    lo = common.make_product("laikago", ["laikago_pace"], 20, seed=21, gid0=0, auto_reset=True, randomizer=rand, max_episode_steps=4)
+    hi = common.make_product("laikago", ["laikago_pace"], N - 20, seed=21, gid0=20, auto_reset=True, randomizer=rand, max_episode_steps=4)
+    full = common.make_product("laikago", ["laikago_pace"], N, seed=21, auto_reset=True, randomizer=rand, max_episode_steps=4)
+    ol, oh, of = lo.reset().clone(), hi.reset().clone(), full.reset().clone()
+    assert torch.equal(torch.cat([ol, oh]), of)
+    for i in range(6):                                   # crosses an episode boundary (time limit 4 steps)
+        rl, rh, rf = lo.step(acts[i][:20].contiguous()), hi.step(acts[i][20:].contiguous()), full.step(acts[i])
+        for x, y, z in zip(rl, rh, rf):
+            assert torch.equal(torch.cat([x, y]), z)
+    for e in (a, b, lo, hi, full):
+        e.close()
+
+
 def test_time_limit_and_termination_thresholds(laikago):
     env, orc = laikago
     env.reset(); orc.reset()
