@@ -1,6 +1,7 @@
 """The list-based drop-in classes (openroborl_b200.compat) keep the reference's env contract."""
 import numpy as np
 import pytest
+import torch
 
 from tests import common
 
@@ -107,3 +108,34 @@ def test_minicheetah_task_name_works(tmp_path):
     with pytest.raises(ValueError, match="no input robot or task"):
         compat.LocomotionGymEnv(None, None)
     env.close()
+
+
+def test_vecenv_facade_resets_inside_step_and_reports_terminal_observations():
+    """VecEnv contract (individual resets inside step, terminal_observation / episode in infos)."""
+    from openroborl_b200.vecenv import VecImitationEnv
+    N = 24
+    clips = common.product_clips(["laikago_pace"])
+    venv = VecImitationEnv("laikago", clips, num_envs=N, seed=3, max_episode_steps=5)
+    ref = common.make_product("laikago", ["laikago_pace"], N, seed=3, max_episode_steps=5)       # same seed, no resets inside step
+    obs = venv.reset()
+    assert obs.shape == (N, 160) and obs.dtype == np.float32 and np.array_equal(obs, ref.reset().cpu().numpy())
+    assert venv.observation_space.shape == (160,) and venv.action_space.shape == (12,)
+    rng = np.random.default_rng(0)
+    ends = 0
+    for t in range(12):
+        act = rng.normal(scale=0.1, size=(N, 12)).astype(np.float32)
+        o, r, d, infos = venv.step(act)
+        assert o.shape == (N, 160) and r.shape == (N,) and d.dtype == bool and len(infos) == N
+        if t < 5:                                    # until the first time limit both envs see the same episode
+            o2, r2, d2 = ref.step(torch.as_tensor(act, device=ref.device))
+            assert np.array_equal(r, r2.cpu().numpy()) and np.array_equal(d, d2.cpu().numpy().astype(bool))
+            for i in range(N):
+                want = infos[i]["terminal_observation"] if d[i] else o[i]
+                assert np.array_equal(want, o2.cpu().numpy()[i])
+        for i in np.nonzero(d)[0]:
+            ends += 1
+            assert infos[i]["episode"]["l"] <= 5 and np.isfinite(infos[i]["episode"]["r"])
+            assert not np.array_equal(infos[i]["terminal_observation"], o[i])        # the returned row already belongs to the new episode
+        assert all("terminal_observation" not in infos[i] for i in np.nonzero(~d)[0])
+    assert ends >= 2 * N                              # the 5-step limit fired at steps 5 and 10 for every robot
+    venv.close(); ref.close()
