@@ -20,7 +20,13 @@ Pinning status
     a fake BulletClient (scripts/fake_bullet.py) that serves the PyBullet calls from
     oracle/rbd.py (tests/test_oracle_trace.py: observations 1e-6, rewards 1e-7, done flags
     and the motion clock exact);
-  - the observation-space bounds serialised inside the reference's policy zips.
+  - the observation-space bounds serialised inside the reference's policy zips;
+  - scripts/make_golden.py -> tests/golden/ref_randomizer_kat.npz: sampled parameters and robot-setter arguments of
+    the reference's own ControllableEnvRandomizerFromConfig (oracle/randomizer.py, bit-exact).
+* Learner arithmetic (oracle/ppo.py: GAE with the reference's index quirk, PPO1 loss with an analytic gradient,
+  MpiAdam update): restated from agents/ppo_imitation.py and stable_baselines/common/mpi_adam.py, which need
+  tensorflow / mpi4py to import -- NOT pinned to outputs of the reference, checked against finite structure only
+  (torch autograd vs the analytic gradient, two-rank averaging).
   The third-party `pybullet_utils.transformations` (pybullet==2.7.3, requirements.txt:5) is
   absent from the container, so its published algorithm is restated in `oracle/xform.py`.
 * Rigid-body arithmetic that the reference delegates to PyBullet 2.7.3
