@@ -663,8 +663,8 @@ __global__ void __launch_bounds__(ORL_BLOCK_THREADS, ORL_STEP_MIN_BLOCKS) orl_st
     const float root_err = dot(dp, dp) + 0.5f * a * a;
     const float3 dv = ld3(S + S_REFVEL) - lin, dw = ld3(S + S_REFVEL + 3) - ang;
     const float rootvel_err = dot(dv, dv) + 0.1f * dot(dw, dw);
-    reward = C.w_pose * expf(-C.s_pose * pose_err) + C.w_vel * expf(-C.s_vel * vel_err) + C.w_ee * expf(-C.s_ee * ee_err) +
-             C.w_root * expf(-C.s_root * root_err) + C.w_rootvel * expf(-C.s_rootvel * rootvel_err);
+    reward = C.w_pose * __expf(-C.s_pose * pose_err) + C.w_vel * __expf(-C.s_vel * vel_err) + C.w_ee * __expf(-C.s_ee * ee_err) +
+             C.w_root * __expf(-C.s_root * root_err) + C.w_rootvel * __expf(-C.s_rootvel * rootvel_err);   // ex2.approx: rel. error < 2e-6
   }
   // Guard (no reference counterpart): a non-finite state ends the episode with reward 0 instead of leaking NaN into
   // observations and statistics.  Velocity clamping keeps the integrator finite; this only catches corrupted input.
@@ -976,7 +976,7 @@ __global__ void orl_reward_terms_kernel(DevEnv E, float* terms) {
   const float rootvel_err = dot(dv, dv) + 0.1f * dot(dw, dw);
   if (valid && leg == 0) {
     float* o = terms + (size_t)i * 5;
-    o[0] = expf(-C.s_pose * pose_err); o[1] = expf(-C.s_vel * vel_err); o[2] = expf(-C.s_ee * ee_err);
-    o[3] = expf(-C.s_root * root_err); o[4] = expf(-C.s_rootvel * rootvel_err);
+    o[0] = __expf(-C.s_pose * pose_err); o[1] = __expf(-C.s_vel * vel_err); o[2] = __expf(-C.s_ee * ee_err);
+    o[3] = __expf(-C.s_root * root_err); o[4] = __expf(-C.s_rootvel * rootvel_err);
   }
 }
