@@ -67,6 +67,9 @@ def motion_clips(ref):
         out[name + "/meta"] = np.array([float(mj["FrameDuration"]), float(mj["LoopMode"] == "Wrap"),
                                         float(bool(mj.get("EnableCycleOffsetPosition", False))),
                                         float(bool(mj.get("EnableCycleOffsetRotation", False)))])
+    # a Clamp-mode clip (the reference library only ships Wrap clips): the pace frames replayed once, no cycle offsets
+    out["synthetic_pace_clamp/frames"] = out["laikago_pace/frames"].copy()
+    out["synthetic_pace_clamp/meta"] = np.array([out["laikago_pace/meta"][0], 0.0, 0.0, 0.0])
     np.savez_compressed(os.path.join(GOLD, "motion_clips.npz"), **out)
     print("motion_clips.npz:", sorted({k.split("/")[0] for k in out}))
 
@@ -113,8 +116,13 @@ def motion_kat(ref):
     mdir = os.path.join(ref, "OpenRoboRL/envs/quadruped_robot/task/motions")
     out = {}
     rng = np.random.RandomState(1234)
-    for name in ("laikago_pace", "laikago_spin", "laikago_hopturn", "minicheetah_trot"):
-        m = motion_data.MotionData(os.path.join(mdir, name + ".txt"))
+    import tempfile
+    clamp = json.load(open(os.path.join(mdir, "laikago_pace.txt")))
+    clamp["LoopMode"] = "Clamp"; clamp["EnableCycleOffsetPosition"] = False; clamp["EnableCycleOffsetRotation"] = False
+    tmpd = tempfile.mkdtemp()
+    json.dump(clamp, open(os.path.join(tmpd, "synthetic_pace_clamp.txt"), "w"))
+    for name in ("laikago_pace", "laikago_spin", "laikago_hopturn", "minicheetah_trot", "synthetic_pace_clamp"):
+        m = motion_data.MotionData(os.path.join(tmpd if name.startswith("synthetic") else mdir, name + ".txt"))
         dur = m.get_duration()
         times = np.concatenate([[0.0, 0.033, 0.5, 0.7, 1.2345, -0.1, dur, 2 * dur, dur - 1e-9],
                                 rng.uniform(-0.3, 25.0, size=200)])
@@ -126,7 +134,7 @@ def motion_kat(ref):
             f0s.append(f0); f1s.append(f1); bl.append(b); cyc.append(m.calc_cycle_count(t))
             poses.append(m.calc_frame(t)); vels.append(m.calc_frame_vel(t)); phases.append(m.calc_phase(t))
         rec.update(f0=np.array(f0s), f1=np.array(f1s), blend=np.array(bl), cycle=np.array(cyc), pose=np.array(poses),
-                   vel=np.array(vels), phase=np.array(phases))
+                   vel=np.array(vels), phase=np.array(phases), is_over=np.array([m.is_over(t) for t in times]))
         for k, v in rec.items():
             out["%s/%s" % (name, k)] = np.asarray(v)
     # pose3d helpers on random unit quaternions

@@ -33,7 +33,7 @@ def cheetah():
 
 
 # ---- (a1-a4) motion tables and frame lookup ---------------------------------------------------------
-@pytest.mark.parametrize("name", ["laikago_pace", "laikago_spin", "laikago_hopturn", "minicheetah_trot"])
+@pytest.mark.parametrize("name", ["laikago_pace", "laikago_spin", "laikago_hopturn", "minicheetah_trot", "synthetic_pace_clamp"])
 def test_motion_lookup_against_reference_golden(name):
     robot = "mini_cheetah" if name.startswith("mini") else "laikago"
     env = common.make_product(robot, [name], 8)
@@ -50,6 +50,32 @@ def test_motion_lookup_against_reference_golden(name):
     scale = np.abs(KAT[name + "/pose"]).max()
     assert np.abs(lk["pose"] - KAT[name + "/pose"]).max() <= 1e-6 * max(scale, 1.0)
     assert np.abs(lk["vel"] - KAT[name + "/vel"]).max() <= 1e-6 * np.abs(KAT[name + "/vel"]).max()
+    env.close()
+
+
+def test_clamp_mode_clip_terminates_when_the_motion_is_over():
+    """a10: done = motion_over for Clamp clips (imitation_task.py:532, motion_data.py:265-276); never for Wrap clips."""
+    N = 32
+    env = common.make_product("laikago", ["synthetic_pace_clamp"], N, seed=4)
+    orc = common.make_oracle("laikago", ["synthetic_pace_clamp"], N, seed=4)
+    env.reset(); orc.reset()
+    dur = float(KAT["synthetic_pace_clamp/duration"])
+    rng = np.random.default_rng(0)
+    over_seen = False
+    for step in range(int(dur / 0.033) + 4):
+        common.sync_oracle_from_product(orc, env.get_state())
+        act = rng.normal(scale=0.05, size=(N, 12)).astype(np.float32)
+        o, r, d = env.step(torch.as_tensor(act, device=env.device))
+        oo, ro, do = orc.step(act.astype(np.float64))
+        st = env.get_state()
+        t_motion = st["substep_counter"] * 1e-3 + st["time_offset"] - np.where(st["warmup"] != 0, 0.25, 0.0)
+        over = t_motion >= dur
+        d = d.cpu().numpy().astype(bool)
+        assert (d | ~over).all()                              # motion over => done
+        safe = (orc._term_margin > 1e-4) & (orc._fall_margin > 1e-5)
+        assert np.array_equal(d[safe], do[safe])
+        over_seen |= bool(over.any())
+    assert over_seen and over.mean() > 0.8 and d[over].all()  # all but the warm-up robots (negative start time) are past the end
     env.close()
 
 

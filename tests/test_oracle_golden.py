@@ -9,7 +9,7 @@ from oracle.motion import MotionLib
 from oracle.env import BUTTER_A, BUTTER_B
 
 KAT = np.load(common.GOLD + "/ref_motion_kat.npz")
-CLIPS = ["laikago_pace", "laikago_spin", "laikago_hopturn", "minicheetah_trot"]
+CLIPS = ["laikago_pace", "laikago_spin", "laikago_hopturn", "minicheetah_trot", "synthetic_pace_clamp"]   # the last one: LoopMode Clamp, generated with the reference module
 
 
 @pytest.mark.parametrize("name", CLIPS)
@@ -106,3 +106,14 @@ def test_observation_bounds_match_policy_zip():
         low, high = env.observation_bounds()
         np.testing.assert_allclose(low, z["obs_low"], rtol=1e-6, atol=1e-6)
         np.testing.assert_allclose(high, z["obs_high"], rtol=1e-6, atol=1e-6)
+
+
+def test_clamp_mode_clip_ends():
+    """LoopMode Clamp (motion_data.py:265-276, 682-718): indices clamp at both ends, the cycle count to [0, 1], is_over."""
+    name = "synthetic_pace_clamp"
+    lib = MotionLib(common.golden_clips_raw([name]))
+    t = KAT[name + "/times"]
+    clip = np.zeros(len(t), dtype=np.int64)
+    assert np.array_equal(lib.is_over(clip, t), KAT[name + "/is_over"])
+    assert KAT[name + "/is_over"].any() and not KAT[name + "/is_over"].all()
+    assert set(np.unique(KAT[name + "/cycle"])) == {0, 1}
