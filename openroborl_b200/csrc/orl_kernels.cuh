@@ -1,9 +1,10 @@
 // The fused control-step kernel, the reset kernel and the parity entry-point kernels.
 //
-// Thread mapping: one lane per leg, 4 lanes (a "quad") per robot, 8 robots per warp, one warp per
-// thread block.  The 8 robots of a warp are one contiguous chunk of the [N][ORL_STRIDE] state array:
-// it is loaded with coalesced float4 accesses into shared memory, the 33 physics substeps run out of
-// registers, and the record plus the 160-float observation rows are written back the same way.
+// Thread mapping: one lane per leg, 4 lanes (a "quad") per robot, 8 robots per warp, 4 independent warps per
+// thread block (they share one copy of the packed model).  The 8 robots of a warp are one contiguous chunk of the
+// [N][ORL_STRIDE] state array: it is fetched into shared memory with one TMA bulk copy, the 33 physics substeps run
+// out of registers (plus a lane-private scratch column in shared memory), and the record plus the 160-float
+// observation rows leave through bulk copies again.
 #pragma once
 #include "orl_math.cuh"
 #include "orl_motion.cuh"

@@ -1,6 +1,6 @@
 // Per-robot state record: one contiguous row of ORL_STRIDE floats per robot in HBM ([N][ORL_STRIDE]).
-// A warp owns 8 consecutive robots = one contiguous 8*ORL_STRIDE*4-byte chunk, loaded and stored with
-// coalesced float4 accesses and staged in shared memory (DESIGN.md "data layout").
+// A warp owns 8 consecutive robots = one contiguous 8*ORL_STRIDE*4-byte chunk, moved to and from shared memory
+// with one TMA bulk copy each way (DESIGN.md "data layout").
 #pragma once
 
 // dynamics state (R/envs/quadruped_robot/task/imitation_task.py:795-829 pose/vel layout)
