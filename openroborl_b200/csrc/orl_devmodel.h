@@ -8,7 +8,7 @@
 
 // collision-point slots per leg on the device: the host's points grouped per body, each group padded to at least
 // ORL_CP_UNROLL entries; the penetration mask is one 32-bit word
-#define ORL_CP_UNROLL 3
+#define ORL_CP_UNROLL 2
 #define ORL_DEV_MAX_CP 32
 
 struct __align__(16) DevJoint {

@@ -144,10 +144,16 @@ static void pack_model(const orl_robot_model& m, DevModel& d) {
         ++pos; ++cnt[g];
       }
     }
-    // primary contact point: the foot-link sphere on body 2 with the largest radius (the toe)
+    // primary contact point: the foot-link sphere on body 2 with the largest radius (the toe); it becomes the LAST
+    // slot of its group, so that the straight-line penetration tests of that group can leave it out
     int prim = -1; float prad = 0.f;
     for (int i = cnt[0] + cnt[1]; i < cnt[0] + cnt[1] + cnt[2]; ++i)
       if (i_from_f(D.cp[i].b.z) != 0 && D.cp[i].a.w > prad) { prad = D.cp[i].a.w; prim = i; }
+    if (prim >= 0) {
+      const int last = cnt[0] + cnt[1] + cnt[2] - 1;
+      const DevCp t = D.cp[prim]; D.cp[prim] = D.cp[last]; D.cp[last] = t;
+      prim = last;
+    }
     // bounds of every body's collision points WITHOUT the primary point (it is evaluated unconditionally):
     // bounding radius about the body origin, and the body-frame bounding box used for the per-substep test
     // "can any point of this body be below the ground?" (lowest possible z = c.z' - sum h_i |R_zi| - rmax)
