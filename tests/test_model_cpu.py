@@ -83,11 +83,12 @@ def test_default_pose_and_constants():
 
 def test_motion_json_round_trip(tmp_path):
     clips = load_clip_library(os.path.join(common.GOLD, "motion_clips.npz"))
-    assert len(clips) == 11
+    assert len(clips) == 12                      # the reference's 11 clips + the synthetic Clamp-mode one
     by = {c.name: c for c in clips}
     assert by["laikago_pace"].frames.shape == (39, 19) and by["laikago_sidesteps"].frames.shape == (146, 19)
     assert by["laikago_spin"].cycle_rot and not by["laikago_pace"].cycle_rot
-    assert all(c.loop_mode == "Wrap" and c.cycle_pos for c in clips)
+    assert all(c.loop_mode == "Wrap" and c.cycle_pos for c in clips if not c.name.startswith("synthetic"))
+    assert by["synthetic_pace_clamp"].loop_mode == "Clamp" and not by["synthetic_pace_clamp"].cycle_pos
     p = tmp_path / "clip.txt"
     p.write_text(by["laikago_spin"].to_json())
     back = MotionClip.load(str(p))
