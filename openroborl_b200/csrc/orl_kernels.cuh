@@ -169,10 +169,17 @@ ORL_DI void build_obs(float* S, float* O, const DevEnv& E, int leg) {
   const double t0 = motion_time(S, C);
   const float3 ref_base = ld3(S + S_REFPOSE);
   // robot.get_base_orientation(): delayed orientation -> euler -> quaternion (minitaur.py:513-527, 630-638)
-  float roll, pitch, yaw;
-  bullet_euler(ldq(S + S_OBSQ), roll, pitch, yaw);
+  // Away from the gimbal branch of Bullet's ZYX euler extraction the heading of that round trip IS the yaw of the
+  // original quaternion (rotated x axis = Rz(yaw) Ry(pitch) e_x, cos(pitch) > 0), so no trigonometry is needed.
+  const Q4 oq = ldq(S + S_OBSQ);
   float sh, ch, shh, chh;                     // sin / cos of -heading and of -heading / 2 (imitation_task.py:270-274)
-  qheading_neg_sincos(bullet_quat_from_euler(roll, pitch, yaw), sh, ch);
+  if (fabsf(-2.f * (oq.x * oq.z - oq.w * oq.y)) < 0.99999f) {
+    qheading_neg_sincos(oq, sh, ch);
+  } else {
+    float roll, pitch, yaw;
+    bullet_euler(oq, roll, pitch, yaw);
+    qheading_neg_sincos(bullet_quat_from_euler(roll, pitch, yaw), sh, ch);
+  }
   half_angle(sh, ch, shh, chh);
   const Q4 inv_rot = q4(0.f, 0.f, shh, chh);
   const double tt = __dadd_rn(t0, __dmul_rn((double)C.tar_steps[leg], C.env_dt));
