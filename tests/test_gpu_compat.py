@@ -139,3 +139,26 @@ def test_vecenv_facade_resets_inside_step_and_reports_terminal_observations():
         assert all("terminal_observation" not in infos[i] for i in np.nonzero(~d)[0])
     assert ends >= 2 * N                              # the 5-step limit fired at steps 5 and 10 for every robot
     venv.close(); ref.close()
+
+
+def test_sim_param_yaml_is_read_relative_to_the_cwd(motion_file, tmp_path, monkeypatch):
+    """quadruped_gym_env.py:158-179: OpenRoboRL/config/pybullet_sim_param.yaml, key quadruped_robot, relative to the cwd."""
+    from openroborl_b200 import compat
+    cfg = tmp_path / "OpenRoboRL" / "config"
+    cfg.mkdir(parents=True)
+    monkeypatch.chdir(tmp_path)
+    (cfg / "pybullet_sim_param.yaml").write_text(
+        "quadruped_robot:\n  enable_rendering: false\n  sim_time_step_s: 0.001\n  enable_rendering_gui: false\n  num_sim_iter_step: 300\n")
+    env = compat.build_env("imitation_learning_laikago", num_robot=2, num_parallel_envs=1, mode="test",
+                           enable_randomizer=False, motion_files=[motion_file], seed=1)
+    assert abs(env._gym_env._env_time_step - 0.033) < 1e-12
+    env.close()
+    (cfg / "pybullet_sim_param.yaml").write_text("quadruped_robot:\n  enable_rendering: false\n  sim_time_step_s: 0.002\n"
+                                                 "  enable_rendering_gui: false\n  num_sim_iter_step: 300\n")
+    with pytest.raises(ValueError):
+        compat.build_env("imitation_learning_laikago", num_robot=2, num_parallel_envs=1, mode="test",
+                         enable_randomizer=False, motion_files=[motion_file], seed=1)
+    (cfg / "pybullet_sim_param.yaml").write_text("other_robot:\n  sim_time_step_s: 0.001\n")
+    with pytest.raises(ValueError):
+        compat.build_env("imitation_learning_laikago", num_robot=2, num_parallel_envs=1, mode="test",
+                         enable_randomizer=False, motion_files=[motion_file], seed=1)
