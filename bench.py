@@ -52,16 +52,37 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.samples, self.stop_flag = index, [], False
 
+    def _nvml_sample(self):
+        """Fast path: NVML through nvidia_ml_py (no process spawn per sample)."""
+        import pynvml as nv
+        if not getattr(self, "_h", None):
+            nv.nvmlInit()
+            self._h = nv.nvmlDeviceGetHandleByIndex(self.index)
+        sm = nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)
+        mx = nv.nvmlDeviceGetMaxClockInfo(self._h, nv.NVML_CLOCK_SM)
+        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+        flag = lambda bit: "Active" if (r & bit) else "Not Active"
+        return [str(sm), str(mx), flag(nv.nvmlClocksThrottleReasonHwSlowdown), flag(nv.nvmlClocksThrottleReasonHwThermalSlowdown),
+                flag(nv.nvmlClocksThrottleReasonSwThermalSlowdown), flag(nv.nvmlClocksThrottleReasonSwPowerCap)]
+
     def run(self):
+        use_nvml = True
         while not self.stop_flag:
             try:
+                if use_nvml:
+                    try:
+                        self.samples.append(self._nvml_sample())
+                        time.sleep(0.01)
+                        continue
+                    except Exception:
+                        use_nvml = False
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
                 if out:
                     self.samples.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.05)
 
     def summary(self):
         if not self.samples:
