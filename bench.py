@@ -96,16 +96,24 @@ class ClockSampler(threading.Thread):
 
 
 def oracle_chunk(args):
-    """Worker of the CPU arm: steps `n` oracle robots `steps` times; returns (robot-steps, seconds)."""
+    """Worker of the CPU arm: steps `n` oracle robots `steps` times on the bench workload (SURVEY 8d C2 action source);
+    returns (robot-steps, seconds)."""
     n, steps, seed = args
     from tests import common
     orc = common.make_oracle("laikago", ["laikago_pace"], n, seed=seed)
-    orc.reset()
+    obs = orc.reset()
     rng = np.random.default_rng(seed)
-    orc.step(rng.normal(scale=0.125, size=(n, 12)))         # warm-up step (imports, caches)
+    sp = orc.spec
+
+    def policy(o):
+        q_ref = np.asarray(o)[:, 84 + 7:84 + 19]                   # joints of the next target frame, URDF order
+        a = (q_ref[:, orc.motor_q] - sp.joint_offset) * sp.joint_dir - sp.init_motor + rng.normal(scale=0.125, size=(n, 12))
+        return np.clip(a, -2 * np.pi, 2 * np.pi)
+
+    obs = orc.step(policy(obs))[0]                                 # warm-up step (imports, caches)
     t0 = time.perf_counter()
     for _ in range(steps):
-        orc.step(rng.normal(scale=0.125, size=(n, 12)))
+        obs = orc.step(policy(obs))[0]
     return n * steps, time.perf_counter() - t0
 
 
