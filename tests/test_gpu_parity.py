@@ -581,7 +581,23 @@ def test_errors_cross_the_boundary_as_python_exceptions():
         env.step(torch.zeros((3, 12), device=env.device))
     with pytest.raises(ValueError):
         env.set_max_episode_steps(0)
+    # raw C-ABI argument checks: null / unaligned observation buffer, ring access without the randomizer
+    import ctypes as C
+    lib, h = env._lib, env._h
+    act = torch.zeros((4, 12), device=env.device)
+    buf = torch.zeros(4 * 160 + 4, device=env.device)
+    rew, done = torch.zeros(4, device=env.device), torch.zeros(4, dtype=torch.uint8, device=env.device)
+    P = lambda t, off=0: C.c_void_p(t.data_ptr() + off)
+    assert lib.orl_step(h, P(act), P(buf, 4), P(rew), P(done), None) == -1          # ORL_ERR_INVALID: 16-byte alignment
+    assert b"aligned" in lib.orl_last_error(h)
+    assert lib.orl_step(h, P(act), None, P(rew), P(done), None) == -1
+    assert lib.orl_step(h, P(act), P(buf), P(rew), P(done), None) == 0
+    assert lib.orl_get_latency_rings_host(h, None, None) == -1 and b"randomizer" in lib.orl_last_error(h)
     env.close()
+    # more clips than the kernel-parameter tables hold
+    clips = common.product_clips(["laikago_pace"]) * 33
+    with pytest.raises(ValueError, match="at most 32"):
+        BatchedImitationEnv("laikago", clips, num_robot=4)
 
 
 def test_policy_rollout_statistics():
