@@ -506,6 +506,18 @@ def test_full_size_properties():
     oa, ra, _ = h0.step(acts[0][:N // 2].contiguous())
     ob, rb, _ = h1.step(acts[0][N // 2:].contiguous())
     assert torch.equal(torch.cat([oa, ob]), outs[0][0]) and torch.equal(torch.cat([ra, rb]), outs[0][1])
+    # the float64 oracle on a slice of the full batch: robots [3000, 3064) keyed by their global ids reset to the same
+    # state (same Philox draws) and take the same first step
+    k0, k = 3000, 64
+    orc = common.make_oracle("laikago", ["laikago_pace"], k, seed=21, gid0=k0)
+    oo = orc.reset()
+    assert np.abs(oo - obs0.cpu().numpy()[k0:k0 + k]).max() <= 2e-5
+    a0 = acts[0].cpu().numpy()[k0:k0 + k].astype(np.float64)
+    o1, r1, d1 = orc.step(a0)
+    pr, pd = outs[0][1].cpu().numpy()[k0:k0 + k], outs[0][2].cpu().numpy()[k0:k0 + k].astype(bool)
+    safe = (orc._term_margin > 1e-4) & (orc._fall_margin > 1e-5)
+    assert np.array_equal(pd[safe], d1[safe]) and safe.mean() > 0.9
+    assert np.median(np.abs(pr - r1)) <= 1e-5 and np.abs(pr - r1).max() <= 2e-3
     for e in (env, env2, h0, h1):
         e.close()
 
