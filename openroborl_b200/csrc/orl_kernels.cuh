@@ -344,6 +344,7 @@ struct LaneCtl {
   int ar;                    // substeps per control step
   int el0;                   // index of the newest observation entry at the first substep of this step (LAT kernels)
   float* ring_q; float* ring_b;   // this robot's rings (LAT kernels)
+  float* qs;                      // this lane's joint angles in the staged record (S_Q + 3 leg); velocities at + (S_QD - S_Q)
   float mac, inv_ar;
   int capture;
   bool first_step;
@@ -420,7 +421,7 @@ ORL_DI void substep(const DevLeg& L, const DevModel& Mo, const PhysParams& P, co
     asm volatile("cp.async.commit_group;" ::: "memory");
   }
   float3 alpha, alin; float qdd[3];
-  leg_dynamics<true, false, true>(L, Mo, P, Rb, D.pos.z, D.ang, D.lin, D.q, D.qd, tau, X, Ctl.rl, alpha, alin, qdd, nullptr);
+  leg_dynamics<true, false, true>(L, Mo, P, Rb, D.pos.z, D.ang, D.lin, D.q, D.qd, tau, X, Ctl.rl, alpha, alin, qdd, nullptr, Ctl.qs, Ctl.qs + (S_QD - S_Q));
   // semi-implicit Euler: velocities first, then positions with the new velocities
   const float3 lin_dot = cross_add(D.ang, D.lin, alin);
   D.ang = clamp3(fma3(P.dt, alpha, D.ang), P.vmax);
@@ -444,6 +445,7 @@ ORL_DI void substep(const DevLeg& L, const DevModel& Mo, const PhysParams& P, co
   for (int k = 0; k < 3; ++k) {
     D.qd[k] = fminf(fmaxf(fmaf(P.dt, qdd[k], D.qd[k]), -P.vmax), P.vmax);
     D.q[k] = fmaf(P.dt, D.qd[k], D.q[k]);
+    Ctl.qs[k] = D.q[k]; Ctl.qs[(S_QD - S_Q) + k] = D.qd[k];        // mirror for the rolled per-joint loop of the next substep
     D.r2[k] = D.r1[k]; D.r1[k] = qm_now[k];
   }
   if (!LAT && s == Ctl.capture) {   // the control observation at the end of the step is 2 substeps old (minitaur.py:336-357)
@@ -526,6 +528,7 @@ __global__ void __launch_bounds__(ORL_BLOCK_THREADS, ORL_STEP_MIN_BLOCKS) orl_st
     fill_scaled_inertia(L, ratios, X + ORL_XI_BASE * ORL_X_STRIDE);
   }
   Ctl.first_step = first_step; Ctl.mac = Mo->b1.w;
+  Ctl.qs = S + S_Q + 3 * leg;
   const int AR = C.action_repeat;
   Ctl.inv_ar = 1.0f / (float)AR; Ctl.capture = AR - 3;
   Ctl.lat_n = 0; Ctl.lat_a = 0.f; Ctl.el0 = substep0 + 1; Ctl.ring_q = nullptr; Ctl.ring_b = nullptr; Ctl.ar = AR;
