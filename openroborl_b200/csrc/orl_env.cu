@@ -293,10 +293,11 @@ extern "C" int orl_create(const orl_config* cfg, const orl_robot_model* model, o
   e->dev.state = e->d_state; e->dev.model = e->d_model; e->dev.stats = e->d_stats;
   e->dev.ring_q = nullptr; e->dev.ring_b = nullptr;
   if (cfg->enable_randomizer) {      // observation history for the randomised control latency
-    CUDA_TRY(e, cudaMalloc(&e->dev.ring_q, (size_t)N * ORL_LAT_RING * 12 * sizeof(float)));
-    CUDA_TRY(e, cudaMalloc(&e->dev.ring_b, (size_t)N * ORL_LAT_RING * 8 * sizeof(float)));
-    CUDA_TRY(e, cudaMemset(e->dev.ring_q, 0, (size_t)N * ORL_LAT_RING * 12 * sizeof(float)));
-    CUDA_TRY(e, cudaMemset(e->dev.ring_b, 0, (size_t)N * ORL_LAT_RING * 8 * sizeof(float)));
+    // one extra row: scratch for the padding quads of a batch that is not a multiple of 8 robots
+    CUDA_TRY(e, cudaMalloc(&e->dev.ring_q, (size_t)(N + 1) * ORL_LAT_RING * 12 * sizeof(float)));
+    CUDA_TRY(e, cudaMalloc(&e->dev.ring_b, (size_t)(N + 1) * ORL_LAT_RING * 8 * sizeof(float)));
+    CUDA_TRY(e, cudaMemset(e->dev.ring_q, 0, (size_t)(N + 1) * ORL_LAT_RING * 12 * sizeof(float)));
+    CUDA_TRY(e, cudaMemset(e->dev.ring_b, 0, (size_t)(N + 1) * ORL_LAT_RING * 8 * sizeof(float)));
   }
   memset(&e->dev.mt, 0, sizeof(e->dev.mt));
   fill_dev_cfg(e);

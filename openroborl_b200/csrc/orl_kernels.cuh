@@ -39,8 +39,8 @@ struct DevEnv {
   double* stats;                      // [4]
   // Randomised control latency (minitaur.py:336-357 with latency in [0, 0.04] s): the last ORL_LAT_RING true
   // observations of every robot, entry E in slot E % ORL_LAT_RING.  Only allocated when the randomizer is on.
-  float* ring_q;                      // [n][ORL_LAT_RING][12] true motor angles
-  float* ring_b;                      // [n][ORL_LAT_RING][8]  base orientation rel. to the init orientation (4), body-frame angular velocity (3)
+  float* ring_q;                      // [n + 1][ORL_LAT_RING][12] true motor angles (row n: scratch for padding quads)
+  float* ring_b;                      // [n + 1][ORL_LAT_RING][8]  base orientation rel. to the init orientation (4), body-frame angular velocity (3)
 };
 // ORL_LAT_RING (orl.h) = 42: latency <= 0.04 s = 40 substeps, entries E-41 .. E are live
 
@@ -81,10 +81,10 @@ ORL_DI void mbar_wait(uint32_t bar) {
     asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
                  : "=r"(ready) : "r"(bar) : "memory");
 }
-// First robot row of this warp and how many of its 8 rows exist (<= 0 for a warp past the end of the batch: it
-// runs on a copy of the last record to stay in the block's barriers and stores nothing).
+// First robot row of this warp and how many of its 8 rows exist (<= 0 for a warp past the end of the batch: it leaves
+// after the block barrier of stage_in; idle quads of a partly filled warp work on a copy of its last record).
 ORL_DI int warp_row0() { return (blockIdx.x * ORL_WARPS_PER_BLOCK + (threadIdx.x >> 5)) * ORL_ROBOTS_PER_WARP; }
-ORL_DI void stage_in(const DevEnv& E, unsigned char* smem, const DevModel*& Mo, float*& st, float*& ob) {
+ORL_DI bool stage_in(const DevEnv& E, unsigned char* smem, const DevModel*& Mo, float*& st, float*& ob) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   Mo = reinterpret_cast<const DevModel*>(smem);
   st = reinterpret_cast<float*>(smem + ORL_SMEM_MODEL_BYTES + warp * ORL_SMEM_WARP_BYTES);
@@ -99,6 +99,9 @@ ORL_DI void stage_in(const DevEnv& E, unsigned char* smem, const DevModel*& Mo, 
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncthreads();
+#ifndef ORL_LOCKSTEP
+  if (nrow <= 0) return false;           // a warp past the end of the batch: nothing to do (no block barrier follows)
+#endif
   if (lane == 0) {
     const uint32_t sbytes = (uint32_t)nsrc * ORL_STRIDE * 4u;
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(sbytes) : "memory");
@@ -116,6 +119,7 @@ ORL_DI void stage_in(const DevEnv& E, unsigned char* smem, const DevModel*& Mo, 
       st[nsrc * ORL_STRIDE + i] = st[(nsrc - 1) * ORL_STRIDE + i % ORL_STRIDE];
     __syncwarp();
   }
+  return true;
 }
 ORL_DI void stage_out(const DevEnv& E, const float* st, const float* ob, float* obs_out) {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to the bulk copy
@@ -197,7 +201,7 @@ ORL_DI void build_obs(float* S, float* O, const DevEnv& E, int leg) {
 // Episode reset of one robot, executed by its quad on the staged record.
 // Minitaur.reset (minitaur.py:232-278) + ImitationTask.reset/_reset_ref_motion/_sync_sim_model
 // (imitation_task.py:166-199, 694-732, 778-793).  `qmask` = the 4 lanes of this quad.
-ORL_DI void reset_robot(float* S, const DevEnv& E, const DevModel& Mo, int gid, int leg, unsigned qmask) {
+ORL_DI void reset_robot(float* S, const DevEnv& E, const DevModel& Mo, int gid, int leg, unsigned qmask, bool valid) {
   const DevCfg& C = E.cfg;
   const DevLeg& L = Mo.leg[leg];
   const int episode = as_int(S[S_EPISODE]);
@@ -236,31 +240,37 @@ ORL_DI void reset_robot(float* S, const DevEnv& E, const DevModel& Mo, int gid, 
   // domain randomizer (Minitaur.reset -> randomize_env, minitaur.py:273-276): ORL_RAND_DRAWS uniforms of this
   // (robot, episode), consumed in the reference's sorted parameter order; u = (word + 0.5) / 2^32
   if (C.randomize) {
-    double val[ORL_RAND_DRAWS];
-    const int first[9] = {0, 1, 3, 11, 12, 13, 15, 16, 28};
+    // No arrays: every draw is mapped and stored where it belongs as soon as its Philox block exists (a value array
+    // indexed by the block counter lived in local memory: 288 bytes of stack in the step kernel).
+    int mot[3], fdraw[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { mot[k] = __float_as_int(L.j[k].m1.z); fdraw[k] = __float_as_int(L.j[k].i3.w); }
+    if (fdraw[0] < 0 && fdraw[1] < 0 && fdraw[2] < 0) S[S_RAND + 6 + leg] = 0.f;
 #pragma unroll 1
     for (int b = 0; b < ORL_RAND_DRAWS / 4; ++b) {
       uint32_t w[4];
       philox4x32((uint32_t)gid, (uint32_t)episode, 2u + (uint32_t)b, 0u, (uint32_t)(C.seed & 0xffffffffull), (uint32_t)(C.seed >> 32), w);
-      for (int j = 0; j < 4; ++j) val[4 * b + j] = ((double)w[j] + 0.5) * (1.0 / 4294967296.0);
-    }
-#pragma unroll 1
-    for (int p = 0; p < 8; ++p)
-      for (int i = first[p]; i < first[p + 1]; ++i) {
-        const double smp = -1.0 + 2.0 * val[i];                                         // np.random.uniform(-1, 1)
-        val[i] = (smp - (-1.0)) / 2.0 * ((double)C.rand_hi[p] - (double)C.rand_lo[p]) + (double)C.rand_lo[p];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = 4 * b + j;                  // draw index; groups start at 0, 1, 3, 11, 12, 13, 15, 16 (sorted parameter names)
+        const int p = (i >= 1) + (i >= 3) + (i >= 11) + (i >= 12) + (i >= 13) + (i >= 15) + (i >= 16);
+        const double u = ((double)w[j] + 0.5) * (1.0 / 4294967296.0);
+        const double smp = -1.0 + 2.0 * u;                                              // np.random.uniform(-1, 1)
+        const float v = (float)((smp - (-1.0)) / 2.0 * ((double)C.rand_hi[p] - (double)C.rand_lo[p]) + (double)C.rand_lo[p]);
+        if (i >= 16) {                                                                  // motor strength of motor i - 16
+          const int m = i - 16;
+          if (m == mot[0] || m == mot[1] || m == mot[2]) S[S_STRENGTH + m] = v;
+        } else if (i >= 3 && i < 11) {                                                  // joint friction draw i - 3
+          if (fdraw[0] == i - 3 || fdraw[1] == i - 3 || fdraw[2] == i - 3) S[S_RAND + 6 + leg] = v;
+        } else if (leg == 0) {
+          // mass: base, legs (13, 14) -> 0, 1; inertia: base, legs (1, 2) -> 2, 3; latency (11) -> 4;
+          // lateral friction of the foot links (12) -> 5, times the plane's; battery (0) and motor damping (15): ignored
+          if (i == 13 || i == 14) S[S_RAND + (i - 13)] = v;
+          else if (i == 1 || i == 2) S[S_RAND + 1 + i] = v;
+          else if (i == 11) S[S_RAND + 4] = v;
+          else if (i == 12) S[S_RAND + 5] = v * C.mu_plane;
+        }
       }
-#pragma unroll
-    for (int k = 0; k < 3; ++k) S[S_STRENGTH + __float_as_int(L.j[k].m1.z)] = (float)val[16 + __float_as_int(L.j[k].m1.z)];
-    float fr = 0.f;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) { const int d = __float_as_int(L.j[k].i3.w); if (d >= 0) fr = (float)val[3 + d]; }
-    S[S_RAND + 6 + leg] = fr;
-    if (leg == 0) {
-      S[S_RAND + 0] = (float)val[13]; S[S_RAND + 1] = (float)val[14];                  // mass: base, legs
-      S[S_RAND + 2] = (float)val[1]; S[S_RAND + 3] = (float)val[2];                    // inertia: base, legs
-      S[S_RAND + 4] = (float)val[11];                                                  // latency
-      S[S_RAND + 5] = (float)val[12] * C.mu_plane;                                     // lateral friction of the foot links
     }
   }
   // _reset_ref_motion
@@ -300,7 +310,9 @@ ORL_DI void reset_robot(float* S, const DevEnv& E, const DevModel& Mo, int gid, 
   if (E.ring_q) {
     // Randomised control latency: the observation history restarts with entry 0 = default pose (receive_obs in
     // Minitaur.reset, minitaur.py:265) and entry 1 = synced pose (receive_obs after _sync_sim_model).
-    float* rq_ = E.ring_q + (size_t)(gid - C.gid0) * (ORL_LAT_RING * 12);
+    // padding quads (robot index past the batch) work on a copy of the last record: their ring traffic goes to the scratch row n
+    const int ring_row = valid ? gid - C.gid0 : C.n;
+    float* rq_ = E.ring_q + (size_t)ring_row * (ORL_LAT_RING * 12);
     const double lat = (double)S[S_RAND + 4] / C.sim_dt;
     const int n = (int)lat;
     const float al = (float)(lat - (double)n);
@@ -314,7 +326,7 @@ ORL_DI void reset_robot(float* S, const DevEnv& E, const DevModel& Mo, int gid, 
       S[S_RING2 + m] = n == 0 ? (1.0f - al) * qm_sync + al * qm_def : qm_def;
     }
     if (leg == 0) {
-      float4* rb = reinterpret_cast<float4*>(E.ring_b + (size_t)(gid - C.gid0) * (ORL_LAT_RING * 8));
+      float4* rb = reinterpret_cast<float4*>(E.ring_b + (size_t)ring_row * (ORL_LAT_RING * 8));
       const Q4 oq = qmul(ldq(S + S_QUAT), qconj(ldq4(Mo.iquat)));
       const float3 ow = qrot(qconj(oq), ld3(S + S_ANG));
       rb[0] = make_float4(0.f, 0.f, 0.f, 1.f); rb[1] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -469,7 +481,7 @@ __global__ void __launch_bounds__(ORL_BLOCK_THREADS, ORL_STEP_MIN_BLOCKS) orl_st
 #endif
   extern __shared__ __align__(16) unsigned char smem[];
   const DevModel* Mo; float* st; float* ob;
-  stage_in(E, smem, Mo, st, ob);
+  if (!stage_in(E, smem, Mo, st, ob)) return;
 #ifdef ORL_PROFILE_RARE
   const long long tk1 = clock64();
 #endif
@@ -537,8 +549,9 @@ __global__ void __launch_bounds__(ORL_BLOCK_THREADS, ORL_STEP_MIN_BLOCKS) orl_st
     const double lat = (double)S[S_RAND + 4] / C.sim_dt;
     Ctl.lat_n = (int)lat;                                              // int(latency / time_step)
     Ctl.lat_a = (float)(lat - (double)Ctl.lat_n);                      // remaining_latency / time_step
-    Ctl.ring_q = E.ring_q + (size_t)robot_c * (ORL_LAT_RING * 12);
-    Ctl.ring_b = E.ring_b + (size_t)robot_c * (ORL_LAT_RING * 8);
+    const int ring_row = valid ? robot : C.n;                          // padding quads: scratch row (rings have n + 1 rows)
+    Ctl.ring_q = E.ring_q + (size_t)ring_row * (ORL_LAT_RING * 12);
+    Ctl.ring_b = E.ring_b + (size_t)ring_row * (ORL_LAT_RING * 8);
     int a, b;
     lat_slots(Ctl.el0, Ctl.lat_n, a, b);
     __syncwarp();                                                      // r1 / r2 were read from these record slots above
@@ -773,7 +786,7 @@ __global__ void __launch_bounds__(ORL_BLOCK_THREADS, ORL_STEP_MIN_BLOCKS) orl_st
   const long long tr0 = clock64();
   const bool any_finish = __any_sync(0xffffffffu, finish);
 #endif
-  if (finish) reset_robot(S, E, *Mo, C.gid0 + robot_c, leg, 0xFu << (lane & ~3));
+  if (finish) reset_robot(S, E, *Mo, C.gid0 + robot_c, leg, 0xFu << (lane & ~3), valid);
 #ifdef ORL_PROFILE_RARE
   __syncwarp();
   if (lane == 0 && any_finish) { atomicAdd(&orl_prof[7], (unsigned long long)(clock64() - tr0)); atomicAdd(&orl_prof[0], 0ull); atomicAdd(&orl_prof[23], 1ull); }
@@ -797,13 +810,13 @@ __global__ void __launch_bounds__(ORL_BLOCK_THREADS, ORL_STEP_MIN_BLOCKS) orl_st
 __global__ void __launch_bounds__(ORL_BLOCK_THREADS) orl_reset_kernel(DevEnv E, const uint8_t* __restrict__ mask, float* __restrict__ obs_out) {
   extern __shared__ __align__(16) unsigned char smem[];
   const DevModel* Mo; float* st; float* ob;
-  stage_in(E, smem, Mo, st, ob);
+  if (!stage_in(E, smem, Mo, st, ob)) return;
   const int lane = threadIdx.x & 31, leg = lane & 3, rw = lane >> 2;
   const int robot = warp_row0() + rw;
   const int robot_c = min(robot, E.cfg.n - 1);
   float* S = st + rw * ORL_STRIDE;
   const bool doit = mask == nullptr || mask[robot_c] != 0;
-  if (doit) reset_robot(S, E, *Mo, E.cfg.gid0 + robot_c, leg, 0xFu << (lane & ~3));
+  if (doit) reset_robot(S, E, *Mo, E.cfg.gid0 + robot_c, leg, 0xFu << (lane & ~3), robot < E.cfg.n);
   __syncwarp();
   build_obs(S, ob + rw * ORL_OBS_SIZE, E, leg);
   stage_out(E, st, ob, obs_out);

@@ -446,6 +446,35 @@ def test_checkpoint_restore_is_bit_exact_and_results_do_not_depend_on_sharding(r
         e.close()
 
 
+@pytest.mark.parametrize("N", [3, 33])
+def test_ragged_batch_with_randomizer_is_deterministic(N):
+    """A batch that is not a multiple of the 8 robots of a warp, train mode (randomizer + randomised control latency):
+    the idle quads of the last warp work on a copy of the last record and must not touch its observation rings.
+    Two runs agree bit for bit, and with the first N robots of a larger batch keyed by the same global ids."""
+    M = 64
+    acts = [torch.as_tensor(np.random.default_rng(100 + i).normal(scale=0.15, size=(M, 12)).astype(np.float32), device="cuda") for i in range(10)]
+
+    def run(n):
+        env = common.make_product("laikago", ["laikago_pace"], n, seed=7, auto_reset=True, randomizer=True, max_episode_steps=4)
+        out = [env.reset().clone()]
+        for a in acts:
+            out.extend(x.clone() for x in env.step(a[:n].contiguous()))
+        rings = env.checkpoint()
+        env.close()
+        return out, rings
+
+    a, ra = run(N)
+    b, rb = run(N)
+    full, _ = run(M)
+    for x, y, z in zip(a, b, full):
+        assert torch.equal(x, y)
+        assert torch.equal(x, z[:N])
+    for k in ra["state"]:
+        assert np.array_equal(ra["state"][k], rb["state"][k]), k
+    for x, y in zip(ra["latency_rings"], rb["latency_rings"]):
+        assert np.array_equal(x, y)
+
+
 def test_time_limit_and_termination_thresholds(laikago):
     env, orc = laikago
     env.reset(); orc.reset()
