@@ -476,6 +476,7 @@ static int check_launch(orl_env* e, const char* what) {
 
 extern "C" int orl_reset(orl_env* e, const uint8_t* mask_dev, float* obs_dev, void* stream) {
   NEED_MOTIONS(e);
+  CUDA_TRY(e, cudaSetDevice(e->device));       // the caller's current device may be another GPU of the box
   const int blocks = (e->cfg.num_robot + ORL_ROBOTS_PER_BLOCK - 1) / ORL_ROBOTS_PER_BLOCK;
   if ((uintptr_t)obs_dev & 15) return fail(e, ORL_ERR_INVALID, "observation buffer must be 16-byte aligned");
   orl_reset_kernel<<<blocks, ORL_BLOCK_THREADS, ORL_SMEM_BYTES, (cudaStream_t)stream>>>(e->dev, mask_dev, obs_dev);
@@ -486,6 +487,7 @@ extern "C" int orl_step(orl_env* e, const float* actions_dev, float* obs_dev, fl
   NEED_MOTIONS(e);
   if (!actions_dev || !obs_dev || !reward_dev || !done_dev) return fail(e, ORL_ERR_INVALID, "null buffer");
   if ((uintptr_t)obs_dev & 15) return fail(e, ORL_ERR_INVALID, "observation buffer must be 16-byte aligned");
+  CUDA_TRY(e, cudaSetDevice(e->device));
   const int blocks = (e->cfg.num_robot + ORL_ROBOTS_PER_BLOCK - 1) / ORL_ROBOTS_PER_BLOCK;
   if (e->dev.ring_q) orl_step_kernel<true><<<blocks, ORL_BLOCK_THREADS, ORL_SMEM_BYTES, (cudaStream_t)stream>>>(e->dev, actions_dev, obs_dev, reward_dev, done_dev);
   else orl_step_kernel<false><<<blocks, ORL_BLOCK_THREADS, ORL_SMEM_BYTES, (cudaStream_t)stream>>>(e->dev, actions_dev, obs_dev, reward_dev, done_dev);
@@ -780,7 +782,9 @@ __global__ void orl_gae_kernel(const float* __restrict__ rew, const float* __res
   if (standardize) {
     const double mean = sum / T;
     const double var = fmax(sum2 / T - mean * mean, 0.0);
-    const float m = (float)mean, inv = (float)(1.0 / sqrt(var));
+    // numpy divides by a zero standard deviation here (T == 1 or a constant advantage: NaN into the PPO loss and the Adam
+    // moments); this kernel only centres such a column -- a stated divergence, the reference never meets the case
+    const float m = (float)mean, inv = var > 0.0 ? (float)(1.0 / sqrt(var)) : 1.0f;
     for (int t = 0; t < T; ++t) { const long idx = (long)t * N + i; adv[idx] = (adv[idx] - m) * inv; }
   }
 }

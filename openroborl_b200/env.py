@@ -73,6 +73,8 @@ class BatchedImitationEnv(object):
         cfg.action_repeat = self.action_repeat
         cfg.max_episode_steps = int(max_episode_steps)
         cfg.auto_reset = int(bool(auto_reset))
+        self.auto_reset = bool(auto_reset)
+        self.config_version = 0
         cfg.enable_cycle_sync = int(bool(self.task["enable_cycle_sync"]))
         cfg.sim_time_step = spec.T_STEP
         cfg.env_time_step = self.action_repeat * spec.T_STEP       # quadruped_gym_env.py:177
@@ -205,9 +207,11 @@ class BatchedImitationEnv(object):
 
     def set_max_episode_steps(self, steps):
         self._check(self._lib.orl_set_max_episode_steps(self._h, int(steps)))
+        self.config_version += 1          # kernel arguments travel by value: captured CUDA graphs are stale now
 
     def set_ref_state_init_prob(self, prob):
         self._check(self._lib.orl_set_ref_state_init_prob(self._h, float(prob)))
+        self.config_version += 1
 
     def stats(self, reset=True):
         out = np.zeros(4, dtype=np.float64)

@@ -19,6 +19,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
+from . import dist as odist
 from .rollout import LOG_STD, MlpGaussianPolicy, RolloutCollector
 
 # trainable variables in graph order (parameter_list of the reference's policy zips); q/* is created by the policy
@@ -82,10 +83,9 @@ class MpiAdam(object):
     def check_synced(self):
         if _world() == 1:
             return
-        theta = self.getflat()
-        root = theta.clone()
-        dist.broadcast(root, src=0)
-        assert torch.equal(root, theta), "MpiAdam: parameters diverged between ranks"
+        # the verdict is all-reduced (MIN), so that EVERY rank raises: a root that carried on alone would hang in its next collective
+        if not odist.check_synced(self.params):
+            raise AssertionError("MpiAdam: parameters diverged between ranks")
 
 
 class PPOLearner(object):
@@ -144,10 +144,16 @@ class PPOLearner(object):
         atarg, ret = seg["adv"], seg["tdlamret"]
         n = obs.shape[0]
         bs = self.optim_batchsize or n
+        nb = (n - bs) // bs + 1 if n >= bs else 0        # full minibatches (Dataset.iterate_once)
+        if _world() > 1:
+            # every adam.update is a collective: ranks with uneven shards (robots % world != 0) must agree on the count
+            t = torch.tensor([nb], dtype=torch.int64, device=obs.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            nb = int(t.item())
         old = {k: v.detach().clone() for k, v in self.policy.p.items()}              # assign_old_eq_new
         for _ in range(self.optim_epochs):
             perm = torch.randperm(n, device=obs.device, generator=self.gen)
-            for s in range(0, n - bs + 1, bs):
+            for s in range(0, nb * bs, bs):
                 idx = perm[s:s + bs]
                 ls = self.losses(old, obs[idx], act[idx], atarg[idx], ret[idx], lrmult)
                 grad = self.flatgrad(ls[0] + ls[1] + ls[2])
@@ -155,7 +161,7 @@ class PPOLearner(object):
         with torch.no_grad():
             tot = torch.zeros(5, dtype=torch.float64, device=obs.device)
             cnt = 0
-            for s in range(0, n - bs + 1, bs):
+            for s in range(0, nb * bs, bs):
                 ls = self.losses(old, obs[s:s + bs], act[s:s + bs], atarg[s:s + bs], ret[s:s + bs], lrmult)
                 tot += torch.stack([x.double() for x in ls]); cnt += 1
             mean = tot / max(cnt, 1)
@@ -175,7 +181,10 @@ class PPOLearner(object):
             seg = col.collect()
             losses = self.update(seg, lrmult)
             stats = col.reduced_stats()                      # [sum reward, sum episode length, episodes, robot steps] over ranks
-            self.num_timesteps += int(seg["total_timestep"]) * _world()          # MPI allreduce of seg["total_timestep"] (:424-426)
+            steps = torch.tensor([int(seg["total_timestep"])], dtype=torch.int64, device=self.policy.device)
+            if _world() > 1:
+                dist.all_reduce(steps, op=dist.ReduceOp.SUM)                     # MPI allreduce of seg["total_timestep"] (:424-426)
+            self.num_timesteps += int(steps.item())
             rec = dict(iteration=iters, timesteps=self.num_timesteps, mean_reward=float(stats[0] / max(stats[3], 1)),
                        ep_len_mean=float(stats[1] / max(stats[2], 1)), episodes=int(stats[2]), **losses)
             history.append(rec)

@@ -7,6 +7,7 @@ here; the post-processing (first-frame xy subtraction, quaternion normalisation/
 velocities, cycle deltas) is done by `orl_load_motions` in the C library.
 """
 import json
+import os
 
 import numpy as np
 
@@ -50,8 +51,17 @@ class MotionClip(object):
                            "Frames": self.frames.tolist()})
 
 
+CLIP_LIBRARY = os.path.join(os.path.dirname(os.path.abspath(__file__)), "assets", "motions", "clips.npz")
+
+
+def bundled_clips(names=None):
+    """The motion clips shipped with the package (the reference's clips under envs/quadruped_robot/task/motions/,
+    re-serialised by scripts/make_golden.py: raw "Frames" + metadata; post-processing happens in orl_load_motions)."""
+    return load_clip_library(CLIP_LIBRARY, names)
+
+
 def load_clip_library(npz_path, names=None):
-    """Clips stored as arrays (tests/golden/motion_clips.npz layout: <name>/frames, <name>/meta)."""
+    """Clips stored as arrays (assets/motions/clips.npz layout: <name>/frames, <name>/meta)."""
     z = np.load(npz_path)
     all_names = sorted({k.split("/")[0] for k in z.files})
     out = []

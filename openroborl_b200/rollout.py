@@ -125,8 +125,10 @@ class RolloutCollector(object):
         # with an auto-reset env nothing in it depends on the host, so it can be captured once and replayed.
         if use_cuda_graph and reset_all_on_any_done:
             raise ValueError("use_cuda_graph needs reset_all_on_any_done=False (the reference's reset-all is a host decision)")
+        if not reset_all_on_any_done and not getattr(env, "auto_reset", True):
+            raise ValueError("reset_all_on_any_done=False needs an auto-reset env (finished robots would be stepped forever)")
         self.use_graph = bool(use_cuda_graph)
-        self._graph, self._seg = None, None
+        self._graph, self._seg, self._graph_version = None, None, None
         N, dev = env.num_robot, env.device
         self.obs_buf = torch.empty((self.T, N, 160), dtype=torch.float32, device=dev)
         self.act_buf = torch.empty((self.T, N, 12), dtype=torch.float32, device=dev)
@@ -146,6 +148,8 @@ class RolloutCollector(object):
     def collect(self):
         if not self.use_graph:
             return self._collect()
+        if self._graph is not None and self._graph_version != (getattr(self.env, "config_version", 0), self.policy.tf32):
+            self._graph = None                       # a setter changed by-value kernel arguments (or the matmul mode) since the capture
         if self._graph is None:                      # warm up on a side stream, then capture the whole segment
             self.noise_buf.normal_(generator=self.gen)
             side = torch.cuda.Stream(device=self.env.device)
@@ -155,6 +159,7 @@ class RolloutCollector(object):
             torch.cuda.current_stream(self.env.device).wait_stream(side)
             torch.cuda.synchronize(self.env.device)
             self.env.stats(reset=True)               # the warm-up pass stepped the env; its episodes are not part of a segment
+            self._graph_version = (getattr(self.env, "config_version", 0), self.policy.tf32)
             self._graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self._graph):
                 self._seg = self._collect()
@@ -193,8 +198,11 @@ class RolloutCollector(object):
                 self.obs.copy_(obs)
         # segment end: the reference bootstraps the last row with 0.0 (imitation_runners.py:93-97)
         self.nextv_buf[T - 1].zero_()
+        # The runner's index arithmetic (ppo_imitation.py:86-90 reads new[t*N + 2j + 1]) only cuts an episode correctly when
+        # every robot restarts together (reset-all: the whole row of flags is equal).  With per-robot restarts inside the
+        # step kernel each robot's recursion has to be cut at ITS OWN restart: flag of robot j in row t + 1.
         adv, ret = gae(self.rew_buf, self.vpred_buf, self.nextv_buf, self.start_buf, self.gamma, self.lam,
-                       reference_index_quirk=True, standardize=True)
+                       reference_index_quirk=self.reset_all, standardize=True)
         N = env.num_robot
         flat = lambda x: x.reshape(T * N, *x.shape[2:])              # time-major interleaved: index t*N + j
         return dict(observations=flat(self.obs_buf), actions=flat(self.act_buf), rewards=flat(self.rew_buf),

@@ -4,7 +4,7 @@
 
 The GPU box has no /root/reference, so everything the tests and bench need from it is frozen here:
 
-* motion_clips.npz     : the RAW "Frames" arrays + metadata of every clip under
+* openroborl_b200/assets/motions/clips.npz : the RAW "Frames" arrays + metadata of every clip under
                          OpenRoboRL/envs/quadruped_robot/task/motions/*.txt (input data in the reference's
                          motion-file format, re-serialised; the JSON loader itself is exercised by re-writing
                          these arrays to JSON at test time).
@@ -70,8 +70,8 @@ def motion_clips(ref):
     # a Clamp-mode clip (the reference library only ships Wrap clips): the pace frames replayed once, no cycle offsets
     out["synthetic_pace_clamp/frames"] = out["laikago_pace/frames"].copy()
     out["synthetic_pace_clamp/meta"] = np.array([out["laikago_pace/meta"][0], 0.0, 0.0, 0.0])
-    np.savez_compressed(os.path.join(GOLD, "motion_clips.npz"), **out)
-    print("motion_clips.npz:", sorted({k.split("/")[0] for k in out}))
+    np.savez_compressed(os.path.join(ROOT, "openroborl_b200", "assets", "motions", "clips.npz"), **out)
+    print("assets/motions/clips.npz:", sorted({k.split("/")[0] for k in out}))
 
 
 class _BoxStub(object):

@@ -9,14 +9,15 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 GOLD = os.path.join(ROOT, "tests", "golden")
 ASSETS = os.path.join(ROOT, "openroborl_b200", "assets")
+CLIPS = os.path.join(ASSETS, "motions", "clips.npz")
 
 URDF = {"laikago": os.path.join(ASSETS, "laikago", "laikago_toes_limits.urdf"),
         "mini_cheetah": os.path.join(ASSETS, "mini_cheetah", "mini_cheetah.urdf")}
 
 
 def golden_clips_raw(names):
-    """Oracle-format clip dicts (raw frames) from tests/golden/motion_clips.npz."""
-    z = np.load(os.path.join(GOLD, "motion_clips.npz"))
+    """Oracle-format clip dicts (raw frames) from the package's clip library (assets/motions/clips.npz)."""
+    z = np.load(CLIPS)
     out = []
     for n in names:
         fd, wrap, cp, cr = z[n + "/meta"]
@@ -27,7 +28,7 @@ def golden_clips_raw(names):
 
 def product_clips(names):
     from openroborl_b200.motion import load_clip_library
-    return load_clip_library(os.path.join(GOLD, "motion_clips.npz"), names)
+    return load_clip_library(CLIPS, names)
 
 
 def load_policy(name):

@@ -125,10 +125,18 @@ def test_rollout_collector_cuda_graph_mode():
             keep = ~st[t + 1]
             assert torch.equal(nv[t][keep], vp[t + 1][keep])
         assert torch.isfinite(seg["adv"]).all() and torch.isfinite(seg["tdlamret"]).all()
-        # GAE of the captured kernel against the oracle on the segment's own buffers
-        a_ref, r_ref = oppo.add_vtarg_and_adv(seg["rewards"].cpu().numpy(), seg["vpred"].cpu().numpy(), seg["nextvpreds"].cpu().numpy(),
-                                              seg["episode_starts"].cpu().numpy().astype(bool), N, 0.95, 0.95)
-        np.testing.assert_allclose(seg["tdlamret"].cpu().numpy(), r_ref, rtol=1e-4, atol=1e-4)
+        # GAE of the captured kernel on the segment's own buffers: with per-robot restarts every robot's recursion is cut
+        # at ITS OWN restart (textbook GAE per robot), not at the runner's index (step*N+i)+(1+i), which only coincides
+        # with it when all robots restart together
+        rew, vpn, nvn = (seg[k].cpu().numpy().reshape(T, N).astype(np.float64) for k in ("rewards", "vpred", "nextvpreds"))
+        es = seg["episode_starts"].cpu().numpy().reshape(T, N).astype(bool)
+        last, want = np.zeros(N), np.zeros((T, N))
+        for t in reversed(range(T)):
+            nonterm = 1.0 - (es[t + 1] if t + 1 < T else np.zeros(N))
+            last = rew[t] + 0.95 * nvn[t] - vpn[t] + 0.95 * 0.95 * nonterm * last
+            want[t] = last
+        np.testing.assert_allclose(seg["tdlamret"].cpu().numpy().reshape(T, N), want + vpn, rtol=1e-4, atol=1e-4)
+        assert es[1:].any()
     # segments continue each other: every robot hits the 6-step limit in each 8-step segment, noise differs between replays
     total = sum(seg["dones"].reshape(T, N).sum(dim=0) for seg in segs)
     assert int(total.min()) >= 3

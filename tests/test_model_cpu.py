@@ -82,7 +82,7 @@ def test_default_pose_and_constants():
 
 
 def test_motion_json_round_trip(tmp_path):
-    clips = load_clip_library(os.path.join(common.GOLD, "motion_clips.npz"))
+    clips = load_clip_library(common.CLIPS)
     assert len(clips) == 12                      # the reference's 11 clips + the synthetic Clamp-mode one
     by = {c.name: c for c in clips}
     assert by["laikago_pace"].frames.shape == (39, 19) and by["laikago_sidesteps"].frames.shape == (146, 19)
