@@ -23,10 +23,11 @@ Pinning status
   - the observation-space bounds serialised inside the reference's policy zips;
   - scripts/make_golden.py -> tests/golden/ref_randomizer_kat.npz: sampled parameters and robot-setter arguments of
     the reference's own ControllableEnvRandomizerFromConfig (oracle/randomizer.py, bit-exact).
-* Learner arithmetic (oracle/ppo.py: GAE with the reference's index quirk, PPO1 loss with an analytic gradient,
-  MpiAdam update): restated from agents/ppo_imitation.py and stable_baselines/common/mpi_adam.py, which need
-  tensorflow / mpi4py to import -- NOT pinned to outputs of the reference, checked against finite structure only
-  (torch autograd vs the analytic gradient, two-rank averaging).
+* Learner arithmetic (oracle/ppo.py): GAE with the reference's index quirk and the MpiAdam update are PINNED to the
+  reference's own functions, executed unmodified under stub tensorflow / mpi4py / stable_baselines modules
+  (scripts/make_ppo_golden.py -> tests/golden/ref_ppo_kat.npz: add_vtarg_and_adv bit for bit, MpiAdam.update on one and
+  two ranks to float32 round-off; tests/test_oracle_ppo_golden.py).  The PPO1 loss needs a TF graph to evaluate and stays
+  a restatement (torch autograd vs the analytic gradient).
   The third-party `pybullet_utils.transformations` (pybullet==2.7.3, requirements.txt:5) is
   absent from the container, so its published algorithm is restated in `oracle/xform.py`.
 * Rigid-body arithmetic that the reference delegates to PyBullet 2.7.3

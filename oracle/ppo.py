@@ -1,5 +1,8 @@
 """Rollout post-processing and the actor network of the reference, restated in NumPy.
 
+Pinned: add_vtarg_and_adv and mpi_adam_update against outputs of the reference's own functions
+(tests/golden/ref_ppo_kat.npz, scripts/make_ppo_golden.py); the PPO1 loss is restated from reading only.
+
 TEST INFRASTRUCTURE (see oracle/__init__.py).  Sources: `OpenRoboRL/agents/ppo_imitation.py:68-93`
 (add_vtarg_and_adv, including its non-terminal index `(step*N+i) + (1+i)`), `:329-338` (per-robot
 advantage standardisation), `OpenRoboRL/agents/imitation_policies.py:44-110` (fixed-std diagonal Gaussian

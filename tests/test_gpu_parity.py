@@ -16,6 +16,21 @@ KAT = np.load(common.GOLD + "/ref_motion_kat.npz")
 PERM = [3, 4, 5, 0, 1, 2] + list(range(6, 18))      # interface [lin, ang, q] <- oracle [ang, lin, q]
 
 
+ERROR_TABLE = {}
+
+
+def dump_error_table():
+    """CUDA-vs-oracle error distributions of test_control_step_matches_oracle, written where gpurun brings files back."""
+    import json, os
+    out = os.path.join(common.ROOT, "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_errors.json"), "w") as f:
+            json.dump(ERROR_TABLE, f, indent=1, sort_keys=True)
+    except OSError:
+        pass
+
+
 @pytest.fixture(scope="module")
 def laikago():
     env = common.make_product("laikago", ["laikago_pace"], 256, seed=5)
@@ -28,6 +43,18 @@ def laikago():
 def cheetah():
     env = common.make_product("mini_cheetah", ["minicheetah_trot"], 128, seed=9)
     orc = common.make_oracle("mini_cheetah", ["minicheetah_trot"], 128, seed=9, phys=common.oracle_phys_from_product(env.phys))
+    yield env, orc
+    env.close()
+
+
+LIBRARY = ["laikago_pace", "laikago_trot", "laikago_spin", "laikago_hopturn", "laikago_sidesteps"]   # BASELINE.json configs[4]
+
+
+@pytest.fixture(scope="module")
+def library():
+    """Config C5: the 5-clip Laikago motion library, random clip and random reference start per episode."""
+    env = common.make_product("laikago", LIBRARY, 320, seed=13)
+    orc = common.make_oracle("laikago", LIBRARY, 320, seed=13, phys=common.oracle_phys_from_product(env.phys))
     yield env, orc
     env.close()
 
@@ -146,13 +173,15 @@ def test_forward_dynamics_with_contact(which, request):
 
 
 # ---- (a5-a7, a16) reset --------------------------------------------------------------------------------
-@pytest.mark.parametrize("which", ["laikago", "cheetah"])
+@pytest.mark.parametrize("which", ["laikago", "cheetah", "library"])
 def test_reset_matches_oracle(which, request):
     env, orc = request.getfixturevalue(which)
     obs = env.reset().cpu().numpy()
     obs_o = orc.reset()
     st = env.get_state()
     assert np.array_equal(st["clip"], orc.clip) and np.array_equal(st["warmup"].astype(bool), orc.warmup)
+    if which == "library":                                             # every clip of the library is drawn, incl. laikago_spin
+        assert set(np.unique(st["clip"])) == set(range(len(LIBRARY)))
     assert np.array_equal(st["time_offset"], orc.time_offset) and np.array_equal(st["prev_phase"], orc.prev_phase)   # FP64 exact
     assert orc.warmup.any() and (~orc.warmup).any()                    # both RSI and warm-up episodes are covered
     for k in ("pos", "quat", "q", "lin", "ang", "qd", "ref_pose", "ref_vel", "origin_pos", "origin_rot"):
@@ -180,13 +209,12 @@ def test_masked_reset_only_touches_masked_robots(laikago):
 
 
 # ---- (a9-a13, a15) full control steps ------------------------------------------------------------------
-@pytest.mark.parametrize("which", ["laikago", "cheetah"])
+@pytest.mark.parametrize("which", ["laikago", "cheetah", "library"])
 def test_control_step_matches_oracle(which, request):
     env, orc = request.getfixturevalue(which)
     env.reset()
     orc.reset()
     rng = np.random.default_rng(4)
-    worst = dict(reward=0.0, obs=0.0)
     for step in range(4):
         common.sync_oracle_from_product(orc, env.get_state())
         # reward terms on IDENTICAL states (no physics in between): <= 1e-5 relative
@@ -202,18 +230,27 @@ def test_control_step_matches_oracle(which, request):
         assert safe.mean() > 0.95 and np.array_equal(d[safe], do[safe])
         assert np.array_equal(st["prev_phase"], orc.prev_phase)                      # FP64 clock, exact
         assert np.array_equal(st["substep_counter"], orc.substep_counter)
-        # 33 FP32 substeps with stiff contact against the FP64 oracle: absolute tolerances, median far below
-        ok = np.abs(st["qd"] - orc.qd).max(axis=1) < 2e-2                            # a contact toggling on a knife edge is allowed to differ
+        # One control step = 33 FP32 substeps with stiff contact against the FP64 oracle from the SAME start state.  The
+        # error distribution per field is recorded (profiles/r02_parity_errors.json, table in DESIGN.md section 6) and the
+        # bounds below are the measured ones with a margin: medians at FP32 round-off, 99th percentiles two orders above, the
+        # maximum only over robots without a contact that toggles on a knife edge (their joint velocities differ by > 2e-2).
+        ok = np.abs(st["qd"] - orc.qd).max(axis=1) < 2e-2
         assert ok.mean() > 0.97
-        assert np.abs(r - ro)[ok].max() <= 1e-4 and np.median(np.abs(r - ro)) <= 5e-6
-        assert np.abs(st["q"] - orc.q)[ok].max() <= 2e-4
-        assert np.abs(st["pos"] - orc.pos)[ok].max() <= 1e-4
-        assert np.abs(o - oo)[ok].max() <= 2e-2 and np.median(np.abs(o - oo)) <= 1e-5
+        errs = {"reward": np.abs(r - ro), "obs": np.abs(o - oo).max(axis=1)}
+        for k in ("pos", "quat", "q", "lin", "ang", "qd"):
+            errs[k] = np.abs(st[k] - getattr(orc, k)).max(axis=1)
+        rec = {k: dict(p50=float(np.percentile(v, 50)), p99=float(np.percentile(v, 99)), max_ok=float(v[ok].max()), max=float(v.max()))
+               for k, v in errs.items()}
+        ERROR_TABLE.setdefault(which, {})["step %d" % (step + 1)] = dict(rec, robots=int(env.num_robot), knife_edge_robots=int((~ok).sum()))
+        # (p50, p99, max over robots without a knife-edge contact); measured r02: reward 3e-7 / 4e-6 / 4e-5, obs 2e-5 / 2e-4 / 4e-3,
+        # pos 4e-8 / 2e-7 / 4e-6, q 1e-6 / 1e-5 / 2e-4, qd 1e-4 / 1e-3 / 1e-2 (library clips incl. laikago_spin are the worst)
+        bound = {"reward": (1e-6, 1e-5, 2e-4), "obs": (5e-5, 5e-4, 2e-2), "pos": (2e-7, 1e-6, 2e-5), "quat": (5e-7, 3e-6, 3e-5),
+                 "q": (5e-6, 5e-5, 1e-3), "lin": (1e-5, 3e-5, 1e-3), "ang": (1e-4, 1e-3, 2e-2), "qd": (5e-4, 5e-3, 2e-2)}
+        for k, (b50, b99, bmax) in bound.items():
+            assert rec[k]["p50"] <= b50 and rec[k]["p99"] <= b99 and rec[k]["max_ok"] <= bmax, (k, rec[k])
         for k in ("act_hist", "filt_x", "filt_y", "prev_filtered", "ref_vel"):
             assert np.abs(st[k] - getattr(orc, k)).max() <= 2e-6 * max(1.0, np.abs(getattr(orc, k)).max()), k
-        worst["reward"] = max(worst["reward"], np.abs(r - ro)[ok].max())
-        worst["obs"] = max(worst["obs"], np.abs(o - oo)[ok].max())
-    print("worst errors over 4 steps:", worst)
+    dump_error_table()
 
 
 def test_velocity_clamp_matches_oracle_and_state_stays_finite(laikago):
@@ -548,6 +585,43 @@ def test_full_size_properties():
     assert np.array_equal(pd[safe], d1[safe]) and safe.mean() > 0.9
     assert np.median(np.abs(pr - r1)) <= 1e-5 and np.abs(pr - r1).max() <= 2e-3
     for e in (env, env2, h0, h1):
+        e.close()
+
+
+def test_full_size_minicheetah_against_oracle_slice():
+    """Config C3: 16384 mini-cheetahs on one GPU.  Determinism, sharding independence and the float64 oracle on a slice of
+    the batch keyed by global robot ids (same Philox draws): reset and two control steps."""
+    N = 16384
+    env = common.make_product("mini_cheetah", ["minicheetah_trot"], N, seed=33)
+    obs0 = env.reset().clone()
+    assert np.abs(env.reward_terms() - 1.0).max() <= 1e-5
+    gen = torch.Generator(device=env.device); gen.manual_seed(2)
+    acts = [torch.randn((N, 12), device=env.device, generator=gen) * 0.1 for _ in range(2)]
+    outs = [tuple(x.clone() for x in env.step(a)) for a in acts]
+    assert all(torch.isfinite(o).all() and torch.isfinite(r).all() for o, r, _ in outs)
+    # two shards reproduce the full batch bit for bit
+    h0 = common.make_product("mini_cheetah", ["minicheetah_trot"], 10000, seed=33, gid0=0)
+    h1 = common.make_product("mini_cheetah", ["minicheetah_trot"], N - 10000, seed=33, gid0=10000)
+    assert torch.equal(torch.cat([h0.reset(), h1.reset()]), obs0)
+    for a, (o, r, d) in zip(acts, outs):
+        oa, ra, da = h0.step(a[:10000].contiguous())
+        ob, rb, db = h1.step(a[10000:].contiguous())
+        assert torch.equal(torch.cat([oa, ob]), o) and torch.equal(torch.cat([ra, rb]), r) and torch.equal(torch.cat([da, db]), d)
+    # oracle slices at both ends and in the middle of the batch
+    for k0 in (0, 9000, N - 64):
+        k = 64
+        orc = common.make_oracle("mini_cheetah", ["minicheetah_trot"], k, seed=33, gid0=k0, phys=common.oracle_phys_from_product(env.phys))
+        oo = orc.reset()
+        assert np.abs(oo - obs0.cpu().numpy()[k0:k0 + k]).max() <= 2e-5
+        for i, (a, (o, r, d)) in enumerate(zip(acts, outs)):
+            o1, r1, d1 = orc.step(a.cpu().numpy()[k0:k0 + k].astype(np.float64))
+            pr, pd = r.cpu().numpy()[k0:k0 + k], d.cpu().numpy()[k0:k0 + k].astype(bool)
+            safe = (orc._term_margin > 1e-4) & (orc._fall_margin > 1e-5)
+            assert np.array_equal(pd[safe], d1[safe]) and safe.mean() > 0.9
+            # the second step starts from two slightly different states (FP32 vs FP64 first step): medians only
+            assert np.median(np.abs(pr - r1)) <= 2e-5 and (i > 0 or np.abs(pr - r1).max() <= 5e-3)
+            assert np.median(np.abs(o.cpu().numpy()[k0:k0 + k] - o1)) <= 5e-5
+    for e in (env, h0, h1):
         e.close()
 
 

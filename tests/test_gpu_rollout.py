@@ -44,6 +44,21 @@ def test_gae_matches_add_vtarg_and_adv():
         np.testing.assert_allclose(adv_c.cpu().numpy(), want, rtol=1e-5, atol=1e-5)
 
 
+def test_gae_kernel_against_the_reference_function():
+    """orl_gae (reference index arithmetic) against outputs of the reference's own add_vtarg_and_adv
+    (tests/golden/ref_ppo_kat.npz, scripts/make_ppo_golden.py)."""
+    from openroborl_b200.rollout import gae
+    kat = np.load(common.GOLD + "/ref_ppo_kat.npz")
+    for c, (T, N) in enumerate(kat["gae/cases"]):
+        T, N = int(T), int(N)
+        g = lambda k: kat["gae/%d/%s" % (c, k)]
+        dev = lambda a, dt=np.float32: torch.as_tensor(np.ascontiguousarray(a.reshape(T, N).astype(dt)), device="cuda")
+        adv, ret = gae(dev(g("rewards")), dev(g("vpred")), dev(g("nextvpreds")), dev(g("episode_starts"), np.uint8), 0.95, 0.95,
+                       reference_index_quirk=True, standardize=False)
+        np.testing.assert_allclose(adv.cpu().numpy().reshape(-1), g("adv"), rtol=2e-6, atol=2e-6)
+        np.testing.assert_allclose(ret.cpu().numpy().reshape(-1), g("tdlamret"), rtol=2e-6, atol=2e-6)
+
+
 def test_policy_forward_and_zip_reader(tmp_path):
     from openroborl_b200.rollout import MlpGaussianPolicy, load_policy_zip
     params = _params()
