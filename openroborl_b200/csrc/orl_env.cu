@@ -5,10 +5,12 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <stdarg.h>
 #include <string.h>
 #include <string>
 #include <vector>
+#include <algorithm>
 
 #include "../../include/orl.h"
 #include "orl_kernels.cuh"
@@ -24,6 +26,8 @@ struct orl_env {
   std::string err;
   // device allocations
   float* d_state;
+  float* d_next_ep; int* d_prepared; int* d_todo; int* d_todo_count;   // episodes prepared ahead of time (auto-reset only)
+  int prep_parity; bool prep_scan;
   DevModel* d_model;
   double* d_stats;
   std::vector<void*> d_motion;     // owned motion-table buffers
@@ -211,7 +215,7 @@ extern "C" int orl_create(const orl_config* cfg, const orl_robot_model* model, o
   orl_env* e = new (std::nothrow) orl_env();
   if (!e) return ORL_ERR_INVALID;
   e->cfg = *cfg; e->model = *model; e->motions_loaded = false; e->launches = 0;
-  e->d_state = nullptr; e->d_model = nullptr; e->d_stats = nullptr;
+  e->d_state = nullptr; e->d_model = nullptr; e->d_stats = nullptr; e->d_next_ep = nullptr; e->d_prepared = nullptr; e->d_todo = nullptr; e->d_todo_count = nullptr; e->prep_parity = 0; e->prep_scan = true;
   e->p_act = e->p_obs = e->p_rew = nullptr; e->p_done = e->p_mask = nullptr;
   e->d_act = e->d_obs = e->d_rew = nullptr; e->d_done = e->d_mask = nullptr;
   e->stream = nullptr;
@@ -292,6 +296,17 @@ extern "C" int orl_create(const orl_config* cfg, const orl_robot_model* model, o
   CUDA_TRY(e, cudaFuncSetAttribute(orl_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ORL_SMEM_BYTES));
   e->dev.state = e->d_state; e->dev.model = e->d_model; e->dev.stats = e->d_stats;
   e->dev.ring_q = nullptr; e->dev.ring_b = nullptr;
+  e->dev.next_ep = nullptr; e->dev.prepared = nullptr; e->dev.prep_blocks = 0;
+  e->dev.todo = nullptr; e->dev.todo_count = nullptr; e->dev.prep_parity = 0; e->dev.prep_scan = 0;
+  if (cfg->auto_reset) {
+    CUDA_TRY(e, cudaMalloc(&e->d_next_ep, (size_t)N * ORL_STRIDE * sizeof(float)));
+    CUDA_TRY(e, cudaMalloc(&e->d_prepared, (size_t)N * sizeof(int)));
+    CUDA_TRY(e, cudaMemset(e->d_prepared, 0, (size_t)N * sizeof(int)));
+    CUDA_TRY(e, cudaMalloc(&e->d_todo, (size_t)4 * N * sizeof(int)));
+    CUDA_TRY(e, cudaMalloc(&e->d_todo_count, 2 * sizeof(int)));
+    CUDA_TRY(e, cudaMemset(e->d_todo_count, 0, 2 * sizeof(int)));
+    e->dev.next_ep = e->d_next_ep; e->dev.prepared = e->d_prepared; e->dev.todo = e->d_todo; e->dev.todo_count = e->d_todo_count;
+  }
   if (cfg->enable_randomizer) {      // observation history for the randomised control latency
     // one extra row: scratch for the padding quads of a batch that is not a multiple of 8 robots
     CUDA_TRY(e, cudaMalloc(&e->dev.ring_q, (size_t)(N + 1) * ORL_LAT_RING * 12 * sizeof(float)));
@@ -314,6 +329,7 @@ extern "C" int orl_destroy(orl_env* e) {
   cudaSetDevice(e->device);
   free_motions(e);
   cudaFree(e->d_state); cudaFree(e->d_model); cudaFree(e->d_stats); cudaFree(e->dev.ring_q); cudaFree(e->dev.ring_b);
+  cudaFree(e->d_next_ep); cudaFree(e->d_prepared); cudaFree(e->d_todo); cudaFree(e->d_todo_count);
   cudaFreeHost(e->p_act); cudaFreeHost(e->p_obs); cudaFreeHost(e->p_rew); cudaFreeHost(e->p_done); cudaFreeHost(e->p_mask);
   cudaFree(e->d_act); cudaFree(e->d_obs); cudaFree(e->d_rew); cudaFree(e->d_done); cudaFree(e->d_mask);
   for (int i = 0; i < ORL_D2H_CHUNKS; ++i) if (e->ev_chunk[i]) cudaEventDestroy(e->ev_chunk[i]);
@@ -445,6 +461,7 @@ extern "C" int orl_load_motions(orl_env* e, const double* frames, const int32_t*
   if ((rc = upload(e, h_cyc, &T.cyc_table))) return rc;
   if ((rc = upload(e, h_warm, &T.warm_pose))) return rc;
   T.n_clips = n_clips;
+  if (e->d_prepared) { CUDA_TRY(e, cudaMemset(e->d_prepared, 0, (size_t)e->cfg.num_robot * sizeof(int))); e->prep_scan = true; }   // other clips, other episodes
   e->motions_loaded = true;
   return ORL_OK;
 }
@@ -479,7 +496,9 @@ extern "C" int orl_reset(orl_env* e, const uint8_t* mask_dev, float* obs_dev, vo
   CUDA_TRY(e, cudaSetDevice(e->device));       // the caller's current device may be another GPU of the box
   const int blocks = (e->cfg.num_robot + ORL_ROBOTS_PER_BLOCK - 1) / ORL_ROBOTS_PER_BLOCK;
   if ((uintptr_t)obs_dev & 15) return fail(e, ORL_ERR_INVALID, "observation buffer must be 16-byte aligned");
-  orl_reset_kernel<<<blocks, ORL_BLOCK_THREADS, ORL_SMEM_BYTES, (cudaStream_t)stream>>>(e->dev, mask_dev, obs_dev);
+  DevEnv d = e->dev;
+  d.prep_parity = e->prep_parity ^ 1;          // queue_for_preparation appends to list prep_parity ^ 1 = the one the next step launch reads
+  orl_reset_kernel<<<blocks, ORL_BLOCK_THREADS, ORL_SMEM_BYTES, (cudaStream_t)stream>>>(d, mask_dev, obs_dev);
   return check_launch(e, "orl_reset_kernel");
 }
 
@@ -489,8 +508,15 @@ extern "C" int orl_step(orl_env* e, const float* actions_dev, float* obs_dev, fl
   if ((uintptr_t)obs_dev & 15) return fail(e, ORL_ERR_INVALID, "observation buffer must be 16-byte aligned");
   CUDA_TRY(e, cudaSetDevice(e->device));
   const int blocks = (e->cfg.num_robot + ORL_ROBOTS_PER_BLOCK - 1) / ORL_ROBOTS_PER_BLOCK;
-  if (e->dev.ring_q) orl_step_kernel<true><<<blocks, ORL_BLOCK_THREADS, ORL_SMEM_BYTES, (cudaStream_t)stream>>>(e->dev, actions_dev, obs_dev, reward_dev, done_dev);
-  else orl_step_kernel<false><<<blocks, ORL_BLOCK_THREADS, ORL_SMEM_BYTES, (cudaStream_t)stream>>>(e->dev, actions_dev, obs_dev, reward_dev, done_dev);
+  DevEnv d = e->dev;
+  // leading blocks that prepare next episodes (they get the lowest block indices: scheduled first when the grid needs several waves)
+  d.prep_blocks = d.next_ep ? std::min(16, std::max(1, (e->cfg.num_robot + 255) / 256)) : 0;
+  { static const char* ov = getenv("ORL_PREP_BLOCKS"); if (ov && d.next_ep) d.prep_blocks = atoi(ov); }   // experiment knob
+  if (d.prep_blocks == 0) { d.next_ep = nullptr; d.prepared = nullptr; d.todo = nullptr; }
+  d.prep_parity = e->prep_parity; d.prep_scan = e->prep_scan ? 1 : 0;
+  e->prep_parity ^= 1; e->prep_scan = false;
+  if (e->dev.ring_q) orl_step_kernel<true><<<blocks + d.prep_blocks, ORL_BLOCK_THREADS, ORL_SMEM_BYTES, (cudaStream_t)stream>>>(d, actions_dev, obs_dev, reward_dev, done_dev);
+  else orl_step_kernel<false><<<blocks + d.prep_blocks, ORL_BLOCK_THREADS, ORL_SMEM_BYTES, (cudaStream_t)stream>>>(d, actions_dev, obs_dev, reward_dev, done_dev);
   return check_launch(e, "orl_step_kernel");
 }
 
@@ -590,6 +616,12 @@ extern "C" int orl_set_ref_state_init_prob(orl_env* e, double prob) {
   if (!e) return ORL_ERR_INVALID;
   e->cfg.ref_state_init_prob = prob;
   e->dev.cfg.rsi_prob = prob;
+  if (e->d_prepared) {                 // prepared episodes drew their start with the old probability
+    CUDA_TRY(e, cudaSetDevice(e->device));
+    CUDA_TRY(e, cudaDeviceSynchronize());
+    CUDA_TRY(e, cudaMemset(e->d_prepared, 0, (size_t)e->cfg.num_robot * sizeof(int)));
+    e->prep_scan = true;
+  }
   return ORL_OK;
 }
 
@@ -627,6 +659,7 @@ extern "C" int orl_set_state_host(orl_env* e, const float* state) {
   CUDA_TRY(e, cudaSetDevice(e->device));
   CUDA_TRY(e, cudaDeviceSynchronize());
   CUDA_TRY(e, cudaMemcpy(e->d_state, state, (size_t)e->cfg.num_robot * ORL_STRIDE * sizeof(float), cudaMemcpyHostToDevice));
+  e->prep_scan = true;                 // episode counters may have moved: the next launch checks every robot's prepared record
   return ORL_OK;
 }
 
@@ -635,6 +668,9 @@ extern "C" int orl_stats(orl_env* e, double out[4], int32_t reset_after) {
   CUDA_TRY(e, cudaSetDevice(e->device));
   CUDA_TRY(e, cudaDeviceSynchronize());
   CUDA_TRY(e, cudaMemcpy(out, e->d_stats, 4 * sizeof(double), cudaMemcpyDeviceToHost));
+#ifdef ORL_DEBUG_PREP
+  { double h[8]; cudaMemcpy(h, e->d_stats, sizeof(h), cudaMemcpyDeviceToHost); fprintf(stderr, "[orl prep] resets from prepared records %.0f, computed inline %.0f\n", h[4], h[5]); }
+#endif
 #ifdef ORL_PROFILE_RARE
   { unsigned long long h[24]; cudaMemcpyFromSymbol(h, orl_prof, sizeof(h));
     fprintf(stderr, "[orl rare] entries %llu trips %llu cycles %llu | loop cycles %llu warp-steps %llu | max cycles %llu max trips %llu\n", h[0], h[1], h[2], h[3], h[4], h[5], h[6]);

@@ -41,6 +41,19 @@ struct DevEnv {
   // observations of every robot, entry E in slot E % ORL_LAT_RING.  Only allocated when the randomizer is on.
   float* ring_q;                      // [n + 1][ORL_LAT_RING][12] true motor angles (row n: scratch for padding quads)
   float* ring_b;                      // [n + 1][ORL_LAT_RING][8]  base orientation rel. to the init orientation (4), body-frame angular velocity (3)
+  // Episodes prepared ahead of time (auto-reset): the record a robot will start its NEXT episode from only depends on
+  // (seed, global robot id, episode index), so a few extra thread blocks of the step kernel compute it while the other
+  // blocks are busy with the substep loop; the in-kernel reset then copies 292 floats instead of running ~2000
+  // instructions of cold code at the very end of the slowest warps (profiles/r02_step_kernel.md "tail").
+  float* next_ep;                     // [n][ORL_STRIDE] record of episode `prepared[i]` (null: feature off)
+  int* prepared;                      // [n] episode index next_ep[i] holds (0: none)
+  int prep_blocks;                    // leading thread blocks of a step launch that prepare episodes
+  // Who needs a new record: every reset appends its robot to the list the NEXT launch consumes (two lists, `prep_parity`
+  // = the one consumed by this launch); prep_scan = 1 makes the prepare blocks walk the whole batch instead (after a
+  // restore or a configuration change, when the lists say nothing).
+  int* todo;                          // [2][2 n] robot indices
+  int* todo_count;                    // [2]
+  int prep_parity, prep_scan;
 };
 // ORL_LAT_RING (orl.h) = 42: latency <= 0.04 s = 40 substeps, entries E-41 .. E are live
 
@@ -83,13 +96,13 @@ ORL_DI void mbar_wait(uint32_t bar) {
 }
 // First robot row of this warp and how many of its 8 rows exist (<= 0 for a warp past the end of the batch: it leaves
 // after the block barrier of stage_in; idle quads of a partly filled warp work on a copy of its last record).
-ORL_DI int warp_row0() { return (blockIdx.x * ORL_WARPS_PER_BLOCK + (threadIdx.x >> 5)) * ORL_ROBOTS_PER_WARP; }
+ORL_DI int warp_row0(const DevEnv& E) { return (((int)blockIdx.x - E.prep_blocks) * ORL_WARPS_PER_BLOCK + (threadIdx.x >> 5)) * ORL_ROBOTS_PER_WARP; }
 ORL_DI bool stage_in(const DevEnv& E, unsigned char* smem, const DevModel*& Mo, float*& st, float*& ob) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   Mo = reinterpret_cast<const DevModel*>(smem);
   st = reinterpret_cast<float*>(smem + ORL_SMEM_MODEL_BYTES + warp * ORL_SMEM_WARP_BYTES);
   ob = st + ORL_ROBOTS_PER_WARP * ORL_STRIDE;
-  const int row0 = warp_row0();
+  const int row0 = warp_row0(E);
   const int nrow = min(ORL_ROBOTS_PER_WARP, E.cfg.n - row0);
   const int src0 = nrow > 0 ? row0 : E.cfg.n - 1, nsrc = nrow > 0 ? nrow : 1;
   const uint32_t bar_model = smem_addr(smem + ORL_SMEM_BAR_OFFSET), bar = bar_model + 8u * (warp + 1);
@@ -125,7 +138,7 @@ ORL_DI void stage_out(const DevEnv& E, const float* st, const float* ob, float* 
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to the bulk copy
   __syncwarp();
   if ((threadIdx.x & 31) == 0) {
-    const int row0 = warp_row0();
+    const int row0 = warp_row0(E);
     const int nrow = min(ORL_ROBOTS_PER_WARP, E.cfg.n - row0);
     if (nrow > 0) {
       bulk_s2g(E.state + (size_t)row0 * ORL_STRIDE, smem_addr(st), (uint32_t)nrow * ORL_STRIDE * 4u);
@@ -201,7 +214,7 @@ ORL_DI void build_obs(float* S, float* O, const DevEnv& E, int leg) {
 // Episode reset of one robot, executed by its quad on the staged record.
 // Minitaur.reset (minitaur.py:232-278) + ImitationTask.reset/_reset_ref_motion/_sync_sim_model
 // (imitation_task.py:166-199, 694-732, 778-793).  `qmask` = the 4 lanes of this quad.
-ORL_DI void reset_robot(float* S, const DevEnv& E, const DevModel& Mo, int gid, int leg, unsigned qmask, bool valid) {
+ORL_DI void reset_robot(float* S, const DevEnv& E, const DevModel& Mo, int gid, int leg, unsigned qmask) {
   const DevCfg& C = E.cfg;
   const DevLeg& L = Mo.leg[leg];
   const int episode = as_int(S[S_EPISODE]);
@@ -307,6 +320,11 @@ ORL_DI void reset_robot(float* S, const DevEnv& E, const DevModel& Mo, int gid, 
     S[S_Q + j] = qj; S[S_QD + j] = vj;
   }
   __syncwarp(qmask);
+}
+// Second half of the reset in train mode: the observation rings of the randomised control latency restart.
+ORL_DI void reset_rings(float* S, const DevEnv& E, const DevModel& Mo, int gid, int leg, unsigned qmask, bool valid) {
+  const DevCfg& C = E.cfg;
+  const DevLeg& L = Mo.leg[leg];
   if (E.ring_q) {
     // Randomised control latency: the observation history restarts with entry 0 = default pose (receive_obs in
     // Minitaur.reset, minitaur.py:265) and entry 1 = synced pose (receive_obs after _sync_sim_model).
@@ -333,6 +351,99 @@ ORL_DI void reset_robot(float* S, const DevEnv& E, const DevModel& Mo, int gid, 
       rb[2] = make_float4(oq.x, oq.y, oq.z, oq.w); rb[3] = make_float4(ow.x, ow.y, ow.z, 0.f);
     }
     __syncwarp(qmask);
+  }
+}
+
+
+// A robot that just started episode e has no prepared record for e + 1 yet: queue it for the next step launch.
+ORL_DI void queue_for_preparation(const DevEnv& E, int robot) {
+  if (!E.todo) return;
+  const int list = E.prep_parity ^ 1;
+  const int slot = atomicAdd(E.todo_count + list, 1);
+  if (slot < 2 * E.cfg.n) E.todo[(size_t)list * 2 * E.cfg.n + slot] = robot;
+}
+// The whole in-kernel reset of one robot: from the prepared record when it is there, else computed on the spot.
+ORL_DI void finish_episode(float* S, const DevEnv& E, const DevModel& Mo, int robot_c, int leg, unsigned qmask, bool valid) {
+  bool ready = false;
+  if (E.next_ep) {
+    int have = 0;
+    if (leg == 0) asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(have) : "l"(E.prepared + robot_c) : "memory");
+    have = __shfl_sync(qmask, have, (threadIdx.x & 31) & ~3);
+    ready = have == as_int(S[S_EPISODE]) + 1;
+  }
+  if (ready) {                                          // (the acquire load of the flag orders the data loads after it)
+    const float4* src = reinterpret_cast<const float4*>(E.next_ep + (size_t)robot_c * ORL_STRIDE);
+    float4* dst = reinterpret_cast<float4*>(S);
+    __syncwarp(qmask);
+    // all loads in flight before the first store (a rolled load-store loop paid one memory latency per float4: 19 in a row)
+    constexpr int kPerLane = (ORL_STRIDE / 4 + 3) / 4;
+    float4 v[kPerLane];
+#pragma unroll
+    for (int k = 0; k < kPerLane; ++k) { const int i = leg + 4 * k; if (i < ORL_STRIDE / 4) v[k] = __ldcg(src + i); }
+#pragma unroll
+    for (int k = 0; k < kPerLane; ++k) { const int i = leg + 4 * k; if (i < ORL_STRIDE / 4) dst[i] = v[k]; }
+    __syncwarp(qmask);
+  } else {
+    reset_robot(S, E, Mo, E.cfg.gid0 + robot_c, leg, qmask);
+  }
+  reset_rings(S, E, Mo, E.cfg.gid0 + robot_c, leg, qmask, valid);
+  if (valid && leg == 0) queue_for_preparation(E, robot_c);
+#ifdef ORL_DEBUG_PREP
+  if (valid && leg == 0) atomicAdd(E.stats + (ready ? 4 : 5), 1.0);
+#endif
+}
+// Thread blocks [0, prep_blocks) of a step launch: one quad per queued robot (or, in scan mode, per robot of the batch
+// whose record is missing) writes the record of that robot's next episode.  Scratch records and a copy of the model
+// live in shared memory like in the worker blocks.
+ORL_DI void prepare_episodes(const DevEnv& E, unsigned char* smem) {
+  const int lane = threadIdx.x & 31, leg = lane & 3, rw = lane >> 2, warp = threadIdx.x >> 5;
+  {
+    const float4* src = reinterpret_cast<const float4*>(E.model);
+    float4* dst = reinterpret_cast<float4*>(smem);
+    for (int i = threadIdx.x; i < (int)(ORL_SMEM_MODEL_BYTES / 16); i += blockDim.x) dst[i] = src[i];
+    __syncthreads();
+  }
+  const DevModel& Mo = *reinterpret_cast<const DevModel*>(smem);
+  float* S = reinterpret_cast<float*>(smem + ORL_SMEM_MODEL_BYTES) + (size_t)(warp * ORL_ROBOTS_PER_WARP + rw) * ORL_STRIDE;
+  const unsigned qmask = 0xFu << (lane & ~3);
+  const int n = E.cfg.n;
+  const int quads = E.prep_blocks * ORL_ROBOTS_PER_BLOCK;
+  const int count = E.prep_scan ? n : min(*reinterpret_cast<volatile const int*>(E.todo_count + E.prep_parity), 2 * n);
+  const int* list = E.todo + (size_t)E.prep_parity * 2 * n;
+  for (int base = ((int)blockIdx.x * ORL_WARPS_PER_BLOCK + warp) * ORL_ROBOTS_PER_WARP; base < count; base += quads) {
+    const int item = base + rw;
+    bool need = false;
+    int episode = 0, robot = 0;
+    if (item < count) {
+      robot = E.prep_scan ? item : __ldcg(list + item);
+      episode = *reinterpret_cast<volatile const int*>(E.state + (size_t)robot * ORL_STRIDE + S_EPISODE);
+      need = *reinterpret_cast<volatile const int*>(E.prepared + robot) != episode + 1;
+    }
+    if (!__any_sync(0xffffffffu, need)) continue;
+    if (need) {
+      const float4* src = reinterpret_cast<const float4*>(E.state + (size_t)robot * ORL_STRIDE);
+      float4* rec = reinterpret_cast<float4*>(S);
+      {
+        constexpr int kPerLane = (ORL_STRIDE / 4 + 3) / 4;
+        float4 v[kPerLane];
+#pragma unroll
+        for (int k = 0; k < kPerLane; ++k) { const int i = leg + 4 * k; if (i < ORL_STRIDE / 4) v[k] = __ldcg(src + i); }
+#pragma unroll
+        for (int k = 0; k < kPerLane; ++k) { const int i = leg + 4 * k; if (i < ORL_STRIDE / 4) rec[i] = v[k]; }      // base: fields a reset leaves alone
+      }
+      __syncwarp(qmask);
+      if (leg == 0) as_int(S[S_EPISODE]) = episode;     // the record may be mid write-back by its own warp: this word decides
+      __syncwarp(qmask);
+      reset_robot(S, E, Mo, E.cfg.gid0 + robot, leg, qmask);
+      __syncwarp(qmask);
+      float4* dst = reinterpret_cast<float4*>(E.next_ep + (size_t)robot * ORL_STRIDE);
+#pragma unroll 1
+      for (int i = leg; i < ORL_STRIDE / 4; i += 4) __stcg(dst + i, rec[i]);
+      __threadfence();                                  // the other three lanes' stores before the release below
+      __syncwarp(qmask);
+      if (leg == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(E.prepared + robot), "r"(episode + 1) : "memory");
+    }
+    __syncwarp();
   }
 }
 
@@ -474,12 +585,13 @@ ORL_DI void substep(const DevLeg& L, const DevModel& Mo, const PhysParams& P, co
 #define ORL_STEP_MIN_BLOCKS (8 / ORL_WARPS_PER_BLOCK)
 #endif
 template <bool LAT>
-__global__ void __launch_bounds__(ORL_BLOCK_THREADS, ORL_STEP_MIN_BLOCKS) orl_step_kernel(DevEnv E, const float* __restrict__ actions, float* __restrict__ obs_out,
-                                                      float* __restrict__ reward_out, uint8_t* __restrict__ done_out) {
+ORL_DI void step_worker(const DevEnv& E, unsigned char* smem, const float* __restrict__ actions, float* __restrict__ obs_out,
+                        float* __restrict__ reward_out, uint8_t* __restrict__ done_out) {
 #ifdef ORL_PROFILE_RARE
   const long long tk0 = clock64();
 #endif
-  extern __shared__ __align__(16) unsigned char smem[];
+  // the list this launch FILLS (resets happen a whole step from now; the prepare blocks read the other one)
+  if (E.todo && (int)blockIdx.x == E.prep_blocks && threadIdx.x == 0) E.todo_count[E.prep_parity ^ 1] = 0;
   const DevModel* Mo; float* st; float* ob;
   if (!stage_in(E, smem, Mo, st, ob)) return;
 #ifdef ORL_PROFILE_RARE
@@ -487,7 +599,7 @@ __global__ void __launch_bounds__(ORL_BLOCK_THREADS, ORL_STEP_MIN_BLOCKS) orl_st
 #endif
   const DevCfg& C = E.cfg;
   const int lane = threadIdx.x & 31, leg = lane & 3, rw = lane >> 2;
-  const int robot = warp_row0() + rw;
+  const int robot = warp_row0(E) + rw;
   const bool valid = robot < C.n;
   const int robot_c = min(robot, C.n - 1);
   float* S = st + rw * ORL_STRIDE;
@@ -495,6 +607,13 @@ __global__ void __launch_bounds__(ORL_BLOCK_THREADS, ORL_STEP_MIN_BLOCKS) orl_st
   float4* X = reinterpret_cast<float4*>(ob) + lane;      // dynamics scratch; aliases the observation staging (dead until build_obs)
   const DevLeg& L = Mo->leg[leg];
   const PhysParams P = C.phys;
+  if (E.next_ep) {
+    // the record a reset at the end of this step would copy: into L2 now (the bench flushes L2 between steps), ~60 us ahead
+    const char* rec = reinterpret_cast<const char*>(E.next_ep + (size_t)robot_c * ORL_STRIDE);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { const int off = (leg + 4 * k) * 128; if (off < ORL_STRIDE * 4) asm volatile("prefetch.global.L2 [%0];" :: "l"(rec + off)); }
+    if (leg == 3) asm volatile("prefetch.global.L2 [%0];" :: "l"(E.prepared + robot_c));
+  }
 
   // ---- registers -----------------------------------------------------------------------------
   float3 pos = ld3(S + S_POS), lin = ld3(S + S_LIN), ang = ld3(S + S_ANG);
@@ -786,7 +905,7 @@ __global__ void __launch_bounds__(ORL_BLOCK_THREADS, ORL_STEP_MIN_BLOCKS) orl_st
   const long long tr0 = clock64();
   const bool any_finish = __any_sync(0xffffffffu, finish);
 #endif
-  if (finish) reset_robot(S, E, *Mo, C.gid0 + robot_c, leg, 0xFu << (lane & ~3), valid);
+  if (finish) finish_episode(S, E, *Mo, robot_c, leg, 0xFu << (lane & ~3), valid);
 #ifdef ORL_PROFILE_RARE
   __syncwarp();
   if (lane == 0 && any_finish) { atomicAdd(&orl_prof[7], (unsigned long long)(clock64() - tr0)); atomicAdd(&orl_prof[0], 0ull); atomicAdd(&orl_prof[23], 1ull); }
@@ -806,17 +925,40 @@ __global__ void __launch_bounds__(ORL_BLOCK_THREADS, ORL_STEP_MIN_BLOCKS) orl_st
 #endif
 }
 
+// The kernel: worker blocks first in the code (the position of the substep loop inside the kernel matters: every 20 KB
+// of code in front of it cost 6 us per step at N = 4096, profiles/r02_step_kernel.md "code placement"), the blocks that
+// prepare episodes after it.
+template <bool LAT>
+__global__ void __launch_bounds__(ORL_BLOCK_THREADS, ORL_STEP_MIN_BLOCKS) orl_step_kernel(DevEnv E, const float* __restrict__ actions, float* __restrict__ obs_out,
+                                                      float* __restrict__ reward_out, uint8_t* __restrict__ done_out) {
+  extern __shared__ __align__(16) unsigned char smem[];
+#ifdef ORL_PAD_KB       // experiment: ORL_PAD_KB x ~2.5 KB of never-executed instructions in front of everything (code placement probe)
+  if (E.cfg.n < 0) {
+    unsigned acc = 0;
+#pragma unroll
+    for (int i = 0; i < ORL_PAD_KB * 64; ++i) { unsigned t; asm volatile("mov.u32 %0, %%clock;" : "=r"(t)); acc ^= t; }
+    if (acc == 12345u) reward_out[0] = 1.f;
+  }
+#endif
+  if ((int)blockIdx.x >= E.prep_blocks) { step_worker<LAT>(E, smem, actions, obs_out, reward_out, done_out); return; }
+  prepare_episodes(E, smem);
+}
+
 // =================================================================================================
 __global__ void __launch_bounds__(ORL_BLOCK_THREADS) orl_reset_kernel(DevEnv E, const uint8_t* __restrict__ mask, float* __restrict__ obs_out) {
   extern __shared__ __align__(16) unsigned char smem[];
   const DevModel* Mo; float* st; float* ob;
   if (!stage_in(E, smem, Mo, st, ob)) return;
   const int lane = threadIdx.x & 31, leg = lane & 3, rw = lane >> 2;
-  const int robot = warp_row0() + rw;
+  const int robot = warp_row0(E) + rw;
   const int robot_c = min(robot, E.cfg.n - 1);
   float* S = st + rw * ORL_STRIDE;
   const bool doit = mask == nullptr || mask[robot_c] != 0;
-  if (doit) reset_robot(S, E, *Mo, E.cfg.gid0 + robot_c, leg, 0xFu << (lane & ~3), robot < E.cfg.n);
+  if (doit) {
+    reset_robot(S, E, *Mo, E.cfg.gid0 + robot_c, leg, 0xFu << (lane & ~3));
+    reset_rings(S, E, *Mo, E.cfg.gid0 + robot_c, leg, 0xFu << (lane & ~3), robot < E.cfg.n);
+    if (robot < E.cfg.n && leg == 0) queue_for_preparation(E, robot);
+  }
   __syncwarp();
   build_obs(S, ob + rw * ORL_OBS_SIZE, E, leg);
   stage_out(E, st, ob, obs_out);
