@@ -40,6 +40,9 @@ struct orl_env {
   cudaStream_t stream;
   cudaEvent_t ev_chunk[ORL_D2H_CHUNKS];
   const float* parity_rand;        // orl_set_dynamics_rand
+  // orl_step_host: the caller's four page-locked buffers of the last call and their device aliases (eight driver queries
+  // per step otherwise: ~5 us of a 130 us call)
+  const void* zc_host[4]; void* zc_dev[4];
 };
 
 static int fail(orl_env* e, int code, const char* fmt, ...) {
@@ -219,6 +222,7 @@ extern "C" int orl_create(const orl_config* cfg, const orl_robot_model* model, o
   e->p_act = e->p_obs = e->p_rew = nullptr; e->p_done = e->p_mask = nullptr;
   e->d_act = e->d_obs = e->d_rew = nullptr; e->d_done = e->d_mask = nullptr;
   e->stream = nullptr;
+  for (int i = 0; i < 4; ++i) { e->zc_host[i] = nullptr; e->zc_dev[i] = nullptr; }
   *out = e;   // returned even on failure so that orl_last_error works; the caller destroys it
   if (cfg->abi_version != ORL_ABI_VERSION) return fail(e, ORL_ERR_INVALID, "ABI version %d != %d", cfg->abi_version, ORL_ABI_VERSION);
   if (cfg->num_robot <= 0) return fail(e, ORL_ERR_INVALID, "num_robot must be positive");
@@ -297,7 +301,7 @@ extern "C" int orl_create(const orl_config* cfg, const orl_robot_model* model, o
   e->dev.state = e->d_state; e->dev.model = e->d_model; e->dev.stats = e->d_stats;
   e->dev.ring_q = nullptr; e->dev.ring_b = nullptr;
   e->dev.next_ep = nullptr; e->dev.prepared = nullptr; e->dev.prep_blocks = 0;
-  e->dev.todo = nullptr; e->dev.todo_count = nullptr; e->dev.prep_parity = 0; e->dev.prep_scan = 0;
+  e->dev.todo = nullptr; e->dev.todo_count = nullptr; e->dev.prep_parity = 0; e->dev.prep_scan = 0; e->dev.obs_split = 0;
   if (cfg->auto_reset) {
     CUDA_TRY(e, cudaMalloc(&e->d_next_ep, (size_t)N * ORL_STRIDE * sizeof(float)));
     CUDA_TRY(e, cudaMalloc(&e->d_prepared, (size_t)N * sizeof(int)));
@@ -502,7 +506,11 @@ extern "C" int orl_reset(orl_env* e, const uint8_t* mask_dev, float* obs_dev, vo
   return check_launch(e, "orl_reset_kernel");
 }
 
+static int step_launch(orl_env* e, const float* actions_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev, void* stream, bool obs_split);
 extern "C" int orl_step(orl_env* e, const float* actions_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev, void* stream) {
+  return step_launch(e, actions_dev, obs_dev, reward_dev, done_dev, stream, false);
+}
+static int step_launch(orl_env* e, const float* actions_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev, void* stream, bool obs_split) {
   NEED_MOTIONS(e);
   if (!actions_dev || !obs_dev || !reward_dev || !done_dev) return fail(e, ORL_ERR_INVALID, "null buffer");
   if ((uintptr_t)obs_dev & 15) return fail(e, ORL_ERR_INVALID, "observation buffer must be 16-byte aligned");
@@ -514,6 +522,7 @@ extern "C" int orl_step(orl_env* e, const float* actions_dev, float* obs_dev, fl
   { static const char* ov = getenv("ORL_PREP_BLOCKS"); if (ov && d.next_ep) d.prep_blocks = atoi(ov); }   // experiment knob
   if (d.prep_blocks == 0) { d.next_ep = nullptr; d.prepared = nullptr; d.todo = nullptr; }
   d.prep_parity = e->prep_parity; d.prep_scan = e->prep_scan ? 1 : 0;
+  d.obs_split = obs_split ? 1 : 0;
   e->prep_parity ^= 1; e->prep_scan = false;
   if (e->dev.ring_q) orl_step_kernel<true><<<blocks + d.prep_blocks, ORL_BLOCK_THREADS, ORL_SMEM_BYTES, (cudaStream_t)stream>>>(d, actions_dev, obs_dev, reward_dev, done_dev);
   else orl_step_kernel<false><<<blocks + d.prep_blocks, ORL_BLOCK_THREADS, ORL_SMEM_BYTES, (cudaStream_t)stream>>>(d, actions_dev, obs_dev, reward_dev, done_dev);
@@ -571,6 +580,17 @@ extern "C" int orl_step_host(orl_env* e, const float* actions, float* obs, float
   CUDA_TRY(e, cudaSetDevice(e->device));
   const int N = e->cfg.num_robot;
   const size_t ab = (size_t)N * 12 * sizeof(float), ob = (size_t)N * ORL_OBS_SIZE * sizeof(float);
+  void* chk = nullptr;
+  if (e->zc_host[0] == actions && e->zc_host[1] == obs && e->zc_host[2] == reward && e->zc_host[3] == done &&
+      cudaHostGetDevicePointer(&chk, obs, 0) == cudaSuccess && chk == e->zc_dev[1]) {
+    // same page-locked buffers as in the previous call (the largest one re-checked): their device aliases are known
+    int rc0 = step_launch(e, (const float*)e->zc_dev[0], (float*)e->zc_dev[1], (float*)e->zc_dev[2], (uint8_t*)e->zc_dev[3], e->stream, true);
+    if (rc0) return rc0;
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    return ORL_OK;
+  }
+  cudaGetLastError();                  // (a failed re-check above leaves a sticky-less error behind)
+  e->zc_host[0] = nullptr;
   const bool pin_a = host_ptr_pinned(actions), pin_o = host_ptr_pinned(obs), pin_r = host_ptr_pinned(reward), pin_d = host_ptr_pinned(done);
   if (pin_a && pin_o && pin_r && pin_d && !((uintptr_t)obs & 15)) {
     // Zero-copy: every buffer is page-locked, so the step kernel reads the actions and writes observation / reward /
@@ -581,7 +601,9 @@ extern "C" int orl_step_host(orl_env* e, const float* actions, float* obs, float
     CUDA_TRY(e, cudaHostGetDevicePointer(&dob, obs, 0));
     CUDA_TRY(e, cudaHostGetDevicePointer(&dr, reward, 0));
     CUDA_TRY(e, cudaHostGetDevicePointer(&dd, done, 0));
-    int rc0 = orl_step(e, (const float*)da, (float*)dob, (float*)dr, (uint8_t*)dd, e->stream);
+    e->zc_host[0] = actions; e->zc_host[1] = obs; e->zc_host[2] = reward; e->zc_host[3] = done;
+    e->zc_dev[0] = da; e->zc_dev[1] = dob; e->zc_dev[2] = dr; e->zc_dev[3] = dd;
+    int rc0 = step_launch(e, (const float*)da, (float*)dob, (float*)dr, (uint8_t*)dd, e->stream, true);
     if (rc0) return rc0;
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));
     return ORL_OK;

@@ -54,6 +54,10 @@ struct DevEnv {
   int* todo;                          // [2][2 n] robot indices
   int* todo_count;                    // [2]
   int prep_parity, prep_scan;
+  // 1: the observation leaves in pieces (the history part right after the action filter, the rest at the end); set when the
+  // observation buffer is mapped HOST memory, where it takes 1.1 of the 2.6 MB per step off the PCIe tail of the launch.
+  // 0: one bulk copy of whole rows per warp at the end (device buffers: six small copies per robot only cost TMA issue slots).
+  int obs_split;
 };
 // ORL_LAT_RING (orl.h) = 42: latency <= 0.04 s = 40 substeps, entries E-41 .. E are live
 
@@ -128,8 +132,14 @@ ORL_DI bool stage_in(const DevEnv& E, unsigned char* smem, const DevModel*& Mo, 
   mbar_wait(bar);
   mbar_wait(bar_model);
   if (nsrc < ORL_ROBOTS_PER_WARP) {        // ragged end: idle quads work on a copy of the last valid record
-    for (int i = lane; i < (ORL_ROBOTS_PER_WARP - nsrc) * ORL_STRIDE; i += 32)
-      st[nsrc * ORL_STRIDE + i] = st[(nsrc - 1) * ORL_STRIDE + i % ORL_STRIDE];
+    // (a rolled float4 copy per idle quad: the flat loop with its `% ORL_STRIDE` unrolled into 300 instructions in front
+    // of the substep loop, and code in front of that loop is not free: profiles/r02_step_kernel.md "code placement")
+    if ((lane >> 2) >= nsrc) {
+      const float4* src = reinterpret_cast<const float4*>(st + (nsrc - 1) * ORL_STRIDE);
+      float4* dst = reinterpret_cast<float4*>(st + (lane >> 2) * ORL_STRIDE);
+#pragma unroll 1
+      for (int i = lane & 3; i < ORL_STRIDE / 4; i += 4) dst[i] = src[i];
+    }
     __syncwarp();
   }
   return true;
@@ -638,6 +648,29 @@ ORL_DI void step_worker(const DevEnv& E, unsigned char* smem, const float* __res
     S[S_FX + m] = act[k]; S[S_FX + 12 + m] = x0; S[S_FY + m] = y; S[S_FY + 12 + m] = y0;
     target[k] = y;
   }
+  // 1b. The part of the observation that does not depend on this step's dynamics leaves NOW: the sensor histories are
+  // shifted (sensor_wrappers.py:131-135, newest first) and the two older IMU / motor-angle readings plus the three last
+  // actions (68 of the 160 floats) go out with three small bulk copies per robot.  When the observation buffer is mapped
+  // host memory (orl_step_host) that is 1.1 of the 2.6 MB per step crossing PCIe behind the substep loop instead of after
+  // the kernel's last warp.  A robot that is reset at the end of the step rewrites its whole row.
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    S[S_ACT + 24 + mi[k]] = S[S_ACT + 12 + mi[k]]; S[S_ACT + 12 + mi[k]] = S[S_ACT + mi[k]]; S[S_ACT + mi[k]] = act[k];
+    S[S_ANGH + 24 + mi[k]] = S[S_ANGH + 12 + mi[k]]; S[S_ANGH + 12 + mi[k]] = S[S_ANGH + mi[k]];
+  }
+  if (leg == 0) {
+#pragma unroll
+    for (int i = 11; i >= 4; --i) S[S_IMU + i] = S[S_IMU + i - 4];
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncwarp();
+  if (E.obs_split && leg == 0 && valid) {
+    float* row = obs_out + (size_t)robot * ORL_OBS_SIZE;
+    bulk_s2g(row + 4, smem_addr(S + S_IMU + 4), 8 * 4);
+    bulk_s2g(row + 12, smem_addr(S + S_ACT), 36 * 4);
+    bulk_s2g(row + 48 + 12, smem_addr(S + S_ANGH + 12), 24 * 4);
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  }
   // 2. physics substeps (quadruped_gym_env.py:220-225)
   // The loop body is kept below the SM's 32 KB instruction cache (one warp per scheduler cannot hide fetch
   // misses): single copy of the contact code, rolled exact tests, SFU trigonometry (profiles/r01_v3_step_kernel.md).
@@ -706,6 +739,7 @@ ORL_DI void step_worker(const DevEnv& E, unsigned char* smem, const float* __res
     atomicMax(&orl_prof[5], rc); atomicMax(&orl_prof[6], rt);
   }
 #endif
+  if (E.obs_split && leg == 0 && valid) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the early observation pieces have left shared memory
   __syncwarp();
   pos = D.pos; quat = D.quat; lin = D.lin; ang = D.ang;
 #pragma unroll
@@ -746,9 +780,7 @@ ORL_DI void step_worker(const DevEnv& E, unsigned char* smem, const float* __res
     S[S_Q + 3 * leg + k] = q[k]; S[S_QD + 3 * leg + k] = qd[k];
     S[S_RING1 + mi[k]] = r1[k]; S[S_RING2 + mi[k]] = r2[k];
     S[S_PREV + mi[k]] = target[k];                                     // minitaur.py:291-292
-    // 3. sensors.on_step (sensor_wrappers.py:131-135): newest first
-    S[S_ACT + 24 + mi[k]] = S[S_ACT + 12 + mi[k]]; S[S_ACT + 12 + mi[k]] = S[S_ACT + mi[k]]; S[S_ACT + mi[k]] = act[k];
-    S[S_ANGH + 24 + mi[k]] = S[S_ANGH + 12 + mi[k]]; S[S_ANGH + 12 + mi[k]] = S[S_ANGH + mi[k]];
+    // 3. sensors.on_step: the newest motor-angle reading (the older entries were shifted in 1b)
     S[S_ANGH + mi[k]] = wrap_pi_fast(r2[k]);
   }
   const int substep1 = substep0 + AR;
@@ -761,7 +793,6 @@ ORL_DI void step_worker(const DevEnv& E, unsigned char* smem, const float* __res
     as_int(S[S_ENVSTEP]) = envstep1;
     float roll, pitch, yaw;
     bullet_euler(obs_q, roll, pitch, yaw);                             // IMUSensor channels R, P, dR, dP
-    for (int i = 11; i >= 4; --i) S[S_IMU + i] = S[S_IMU + i - 4];
     S[S_IMU + 0] = roll; S[S_IMU + 1] = pitch; S[S_IMU + 2] = obs_w.x; S[S_IMU + 3] = obs_w.y;
   }
 #ifdef ORL_PROFILE_RARE
@@ -919,7 +950,22 @@ ORL_DI void step_worker(const DevEnv& E, unsigned char* smem, const float* __res
   if (lane == 0) atomicAdd(&orl_prof[22], (unsigned long long)(clock64() - to0));
   const long long ts0 = clock64();
 #endif
-  stage_out(E, st, ob, obs_out);
+  // late part of the observation: newest IMU / motor-angle readings and the target frames; the whole row after a reset
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncwarp();
+  if (E.obs_split && leg == 0 && valid) {
+    float* row = obs_out + (size_t)robot * ORL_OBS_SIZE;
+    if (finish) {
+      bulk_s2g(row, smem_addr(O), ORL_OBS_SIZE * 4);
+    } else {
+      bulk_s2g(row, smem_addr(S + S_IMU), 4 * 4);
+      bulk_s2g(row + 48, smem_addr(S + S_ANGH), 12 * 4);
+      bulk_s2g(row + 84, smem_addr(O + 84), 76 * 4);
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  }
+  stage_out(E, st, ob, E.obs_split ? nullptr : obs_out);
+  if (E.obs_split && leg == 0 && valid) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 #ifdef ORL_PROFILE_RARE
   if (lane == 0) { atomicAdd(&orl_prof[14], (unsigned long long)(clock64() - ts0)); atomicAdd(&orl_prof[15], (unsigned long long)(ts0 - tend_loop)); }
 #endif
