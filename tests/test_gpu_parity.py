@@ -123,6 +123,30 @@ def test_motion_lookup_library_random_times():
 
 
 # ---- (a8, a14) kinematics and dynamics ------------------------------------------------------------------
+def test_cuda_fk_against_the_reference_closed_form_leg_model(cheetah):
+    """a8 against the one piece of forward kinematics the reference states itself: the analytic 3-link leg of
+    R/envs/quadruped_robot/task/motions/trans2minicheetah.m:28-30, 146-161 (the model its mini-cheetah clip was made with).
+    Toe position from orl_fk relative to the hip joint, random base poses and joint angles, <= 1e-5 relative."""
+    from openroborl_b200 import retarget as rt
+    env, orc = cheetah
+    rng = np.random.default_rng(7)
+    n = 256
+    pose, _ = common.random_states(rng, n, "mini_cheetah")
+    pose[:, 7:] = rng.uniform(-1.0, 1.0, size=(n, 12)).astype(np.float32)
+    p64 = pose.astype(np.float64)
+    com = env.fk(pose)                                                  # world COM of every link (getLinkState()[0])
+    k = orc.tree.fk(p64[:, 0:3], p64[:, 3:7], p64[:, 7:])               # hip joint origins (fixed in the base) from the URDF tree
+    from oracle import xform as xf
+    Rb = xf.quat_to_matrix(p64[:, 3:7])
+    for l, side in enumerate((-1.0, 1.0, -1.0, 1.0)):                   # fr, fl, hr, hl
+        hip, toe = 1 + 4 * l, 4 + 4 * l
+        rel_world = com[:, toe - 1] - k["x"][:, hip]                    # the toe link's inertial origin is its own origin in the fixture
+        rel = np.einsum("nji,nj->ni", Rb, rel_world)                    # into the base frame
+        want = rt.leg_fk(p64[:, 7 + 3 * l:10 + 3 * l] * rt.MINI_SIGNS[3 * l:3 * l + 3], *rt.MINI_CHEETAH_LEG, side)
+        assert np.abs(rel - want).max() <= 1e-5 * np.abs(want).max() + 2e-6      # float32 world coordinates up to 3 m from the origin
+
+
+
 @pytest.mark.parametrize("which", ["laikago", "cheetah"])
 def test_fk_mass_matrix_inverse_dynamics(which, request):
     env, orc = request.getfixturevalue(which)
