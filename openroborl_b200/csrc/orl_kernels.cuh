@@ -617,13 +617,6 @@ ORL_DI void step_worker(const DevEnv& E, unsigned char* smem, const float* __res
   float4* X = reinterpret_cast<float4*>(ob) + lane;      // dynamics scratch; aliases the observation staging (dead until build_obs)
   const DevLeg& L = Mo->leg[leg];
   const PhysParams P = C.phys;
-  if (E.next_ep) {
-    // the record a reset at the end of this step would copy: into L2 now (the bench flushes L2 between steps), ~60 us ahead
-    const char* rec = reinterpret_cast<const char*>(E.next_ep + (size_t)robot_c * ORL_STRIDE);
-#pragma unroll
-    for (int k = 0; k < 3; ++k) { const int off = (leg + 4 * k) * 128; if (off < ORL_STRIDE * 4) asm volatile("prefetch.global.L2 [%0];" :: "l"(rec + off)); }
-    if (leg == 3) asm volatile("prefetch.global.L2 [%0];" :: "l"(E.prepared + robot_c));
-  }
 
   // ---- registers -----------------------------------------------------------------------------
   float3 pos = ld3(S + S_POS), lin = ld3(S + S_LIN), ang = ld3(S + S_ANG);
