@@ -811,6 +811,7 @@ ORL_DI void step_worker(const DevEnv& E, unsigned char* smem, const float* __res
     float ss, cs, sr, cr;
     qheading_neg_sincos(qmul(quat, inv_def), ss, cs);
     qheading_neg_sincos(qmul(rq, inv_def), sr, cr);
+#pragma unroll 1              // one copy of the body: once-per-step code pays per fetched instruction
     for (int e = 0; e < L.meta.x; ++e) {
       const float4 ee = L.ee[e];
       const int kb = __float_as_int(ee.w);

@@ -172,6 +172,22 @@ ORL_DI Q4 qslerp(Q4 a, Q4 b, float f) {
   wa = sinf((1.f - f) * ang) * isin; wb = sinf(f * ang) * isin;
   return q4(wa * a.x + wb * b.x, wa * a.y + wb * b.y, wa * a.z + wb * b.z, wa * a.w + wb * b.w);
 }
+// sin / cos of a DOUBLE angle of any magnitude (cycle headings: cycle count x heading per cycle): reduction to
+// [-pi/4, pi/4] in FP64 (the reference computes these in double; rounding the angle to float first cost up to 1.5e-5 at
+// |x| = 300), then degree-9 / degree-8 polynomials in float: absolute error 1e-7, 20 instructions against the ~190 of
+// sincosf with its large-argument path.
+ORL_DI void sincos_f64arg(double x, float& s, float& c) {
+  const int k = __double2int_rn(x * 0.63661977236758134308);
+  const double kd = (double)k;
+  const float r = (float)fma(-kd, 6.123233995736766e-17, fma(-kd, 1.5707963267948966, x));
+  const float r2 = r * r;
+  const float sr = fmaf(r * r2, fmaf(r2, fmaf(r2, fmaf(r2, 1.f / 362880.f, -1.f / 5040.f), 1.f / 120.f), -1.f / 6.f), r);
+  const float cr = fmaf(r2, fmaf(r2, fmaf(r2, fmaf(r2, 1.f / 40320.f, -1.f / 720.f), 1.f / 24.f), -0.5f), 1.f);
+  const bool swap = k & 1;
+  const float ss = swap ? cr : sr, cc = swap ? sr : cr;
+  s = (k & 2) ? -ss : ss;
+  c = ((k + 1) & 2) ? -cc : cc;
+}
 
 // ---- Philox4x32-10 (same contract as oracle/philox.py) --------------------------------------
 ORL_DI void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4]) {

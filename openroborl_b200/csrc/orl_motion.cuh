@@ -75,7 +75,7 @@ ORL_DI void motion_cycle_offset(const MotionTables& T, int clip, int cycle, floa
   if (fl & 4) {
     const double h = __dmul_rn((double)cycle, T.dheading[clip]);
     float sh, ch;
-    sincosf((float)(0.5 * h), &sh, &ch);
+    sincos_f64arg(0.5 * h, sh, ch);
     off_rot = q4(0.f, 0.f, sh, ch);
     s = 2.f * sh * ch; c = ch * ch - sh * sh;
   }
@@ -86,9 +86,10 @@ ORL_DI void motion_cycle_offset(const MotionTables& T, int clip, int cycle, floa
         const float* t = T.cyc_table + ((size_t)clip * ORL_CYCLE_TABLE + cycle) * 3;
         off_pos = v3(t[0], t[1], t[2]);
       } else {
+#pragma unroll 1              // never taken for clips shorter than ORL_CYCLE_TABLE cycles: keep it small
         for (int i = 0; i < cycle; ++i) {
           float si, ci;
-          sincosf((float)((double)i * T.dheading[clip]), &si, &ci);
+          sincos_f64arg((double)i * T.dheading[clip], si, ci);
           off_pos += qrot_z(si, ci, dp);
         }
       }
