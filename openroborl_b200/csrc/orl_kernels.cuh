@@ -788,6 +788,18 @@ ORL_DI void step_worker(const DevEnv& E, unsigned char* smem, const float* __res
     bullet_euler(obs_q, roll, pitch, yaw);                             // IMUSensor channels R, P, dR, dP
     S[S_IMU + 0] = roll; S[S_IMU + 1] = pitch; S[S_IMU + 2] = obs_w.x; S[S_IMU + 3] = obs_w.y;
   }
+  // 3b. host buffers: the newest IMU / motor-angle readings (16 floats) cross PCIe behind the rest of the once-per-step code
+  // instead of after it (a robot that is reset below waits for these copies and rewrites its whole row)
+  if (E.obs_split) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (leg == 0 && valid) {
+      float* row = obs_out + (size_t)robot * ORL_OBS_SIZE;
+      bulk_s2g(row, smem_addr(S + S_IMU), 4 * 4);
+      bulk_s2g(row + 48, smem_addr(S + S_ANGH), 12 * 4);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  }
 #ifdef ORL_PROFILE_RARE
   long long tsec = clock64(); if (lane == 0) atomicAdd(&orl_prof[8], (unsigned long long)(tsec - tend_loop));
 #endif
@@ -930,7 +942,13 @@ ORL_DI void step_worker(const DevEnv& E, unsigned char* smem, const float* __res
   const long long tr0 = clock64();
   const bool any_finish = __any_sync(0xffffffffu, finish);
 #endif
-  if (finish) finish_episode(S, E, *Mo, robot_c, leg, 0xFu << (lane & ~3), valid);
+  if (finish) {
+    if (E.obs_split) {           // the early pieces of this row have landed before the record changes and the whole row follows
+      if (leg == 0 && valid) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      __syncwarp(0xFu << (lane & ~3));
+    }
+    finish_episode(S, E, *Mo, robot_c, leg, 0xFu << (lane & ~3), valid);
+  }
 #ifdef ORL_PROFILE_RARE
   __syncwarp();
   if (lane == 0 && any_finish) { atomicAdd(&orl_prof[7], (unsigned long long)(clock64() - tr0)); atomicAdd(&orl_prof[0], 0ull); atomicAdd(&orl_prof[23], 1ull); }
@@ -952,8 +970,6 @@ ORL_DI void step_worker(const DevEnv& E, unsigned char* smem, const float* __res
     if (finish) {
       bulk_s2g(row, smem_addr(O), ORL_OBS_SIZE * 4);
     } else {
-      bulk_s2g(row, smem_addr(S + S_IMU), 4 * 4);
-      bulk_s2g(row + 48, smem_addr(S + S_ANGH), 12 * 4);
       bulk_s2g(row + 84, smem_addr(O + 84), 76 * 4);
     }
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");

@@ -24,9 +24,10 @@ def main():
     ap.add_argument("--horizon", type=int, default=32)
     ap.add_argument("--randomizer", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--tf32", action="store_true", help="TF32 policy GEMMs (default: fp32 like the reference's TF graph)")
     args = ap.parse_args()
     rank, local, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
-    os.environ["NCCL_DEBUG"] = "WARN"
+    os.environ.setdefault("NCCL_DEBUG", "WARN")
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -36,7 +37,7 @@ def main():
                               gid0=rank * N, auto_reset=True, max_episode_steps=600, enable_randomizer=args.randomizer)
     z = np.load(os.path.join(ROOT, "tests", "golden", "policy_laikago_pace.npz"))
     params = {k.rsplit("_", 1)[0] + "/" + k.rsplit("_", 1)[1]: z[k] for k in z.files if k.rsplit("_", 1)[-1] in ("w", "b")}
-    pol = rollout.MlpGaussianPolicy(params, env.device, tf32=True)
+    pol = rollout.MlpGaussianPolicy(params, env.device, tf32=args.tf32)
     col = rollout.RolloutCollector(env, pol, args.horizon, reset_all_on_any_done=False, seed=rank, use_cuda_graph=not args.no_graph)
 
     def sync():
