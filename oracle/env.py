@@ -28,7 +28,10 @@ DEFAULT_TASK = dict(
     root_velocity_weight=0.1, pose_err_scale=5.0, velocity_err_scale=0.1, end_effector_err_scale=40.0,
     end_effector_height_err_scale=3.0, root_pose_err_scale=20.0, root_velocity_err_scale=2.0,
     tar_frame_steps=(1, 2, 10, 30), ref_state_init_prob=0.9, warmup_time=0.25, enable_cycle_sync=True,
-    dist_fail_threshold=1.0, rot_fail_threshold=0.5 * np.pi)
+    dist_fail_threshold=1.0, rot_fail_threshold=0.5 * np.pi,
+    # options run.py leaves at their defaults (imitation_task.py:36-57)
+    weight=1.0, enable_rand_init_time=True, clip_time_min=np.inf, clip_time_max=np.inf,
+    perturb_init_state_prob=0.0, tar_obs_noise=None)
 
 # action_filter.py:42-44 + scipy.signal.butter(2, [4/(0.5*fs)]) at fs = 1/(0.001*33); SURVEY.md App. B
 BUTTER_B = np.array([0.10669309218914798, 0.21338618437829596, 0.10669309218914798])
@@ -101,6 +104,10 @@ class OracleEnv(object):
         self.clip = np.zeros(N, dtype=np.int64); self.time_offset = np.zeros(N); self.warmup = np.zeros(N, dtype=bool)
         self.origin_pos = np.zeros((N, 3)); self.origin_rot = np.tile(np.array([0.0, 0, 0, 1]), (N, 1))
         self.prev_phase = np.zeros(N)
+        self.clip_change_time = np.full(N, np.inf); self.clip_changes = np.zeros(N, dtype=np.int64)
+        # replay of draws recorded from the reference's classes (tests): per robot a list of (kind, value) in the
+        # reference's call order; None: the keyed Philox draws of the product's contract (oracle/philox.py)
+        self.replay = None
         self.ref_pose = np.zeros((N, 19)); self.ref_vel = np.zeros((N, 18))
         self.motor_strength = np.ones((N, 12))
         # domain randomizer state (oracle/randomizer.py); identity when it is off
@@ -114,6 +121,20 @@ class OracleEnv(object):
         self.default_pose = np.concatenate([s.init_pos, s.init_quat,
                                             (s.init_motor + s.joint_offset) * s.joint_dir])  # minitaur.py:1190-1194
         self._urdf_from_motor = np.argsort(self.motor_q)
+
+    # ---- random draws of the task options -------------------------------------------------
+    def _draw(self, kind, values, mask):
+        """`values`: the keyed Philox draw of every robot, already mapped to the reference call's result
+        (np.random.uniform(lo, hi) = lo + (hi - lo) u, randn * std + mean, randint).  In replay mode the robots in
+        `mask` take the next recorded reference draw instead (kind 'u' / 'i' / 'n' must match the record)."""
+        if self.replay is None:
+            return values
+        out = np.array(values, dtype=np.int64 if kind == "i" else np.float64)
+        for i in np.nonzero(mask)[0]:
+            k, v = self.replay[i].pop(0)
+            assert k == kind, (i, k, kind)
+            out[i] = v
+        return out
 
     # ---- space conversions (minitaur.py:549-553, 575-578, 755-756) ------------------------
     def motor_angles_true(self):
@@ -265,6 +286,8 @@ class OracleEnv(object):
         off = np.where(self.warmup, 0 + (self.task["warmup_time"] - 0) * u_time, 0 + (dur - 0) * u_time)  # :1103-1123
         if time_offset is not None:      # replay of recorded reference draws (tests): exact offset instead of dur * u
             off = np.asarray(time_offset, dtype=np.float64)
+        if not self.task["enable_rand_init_time"]:                               # :1104-1105
+            off = np.zeros(N)
         self.time_offset = np.where(m, off, self.time_offset)
         self.episode = np.where(m, self.episode + 1, self.episode)
         # _reset_ref_motion :694-732
@@ -280,15 +303,56 @@ class OracleEnv(object):
         self.ref_pose = np.where(mm, self.calc_ref_pose(time), self.ref_pose)
         self.ref_vel = np.where(mm, self.calc_ref_vel(time), self.ref_vel)
         self.prev_phase = np.where(m, self.lib.calc_phase(self.clip, time), self.prev_phase)
+        # _reset_clip_change_time :1057-1067 (the last call of _reset_ref_motion, :730)
+        tk = self.task
+        switching = np.isfinite(tk["clip_time_min"]) and np.isfinite(tk["clip_time_max"])
+        need_opt = switching or tk["perturb_init_state_prob"] > 0.0
+        if need_opt:
+            u_perturb, u_dur, z, axis = philox.option_reset_draws(self.seed, self.gid, self.episode - 1)
+        change_time = np.full(N, np.inf)
+        if switching:
+            change_time = time + self._draw("u", tk["clip_time_min"] + (tk["clip_time_max"] - tk["clip_time_min"]) * u_dur, m)
+        self.clip_change_time = np.where(m, change_time, self.clip_change_time)
+        self.clip_changes = np.where(m, 0, self.clip_changes)
+        # :192-195
+        pose, vel = self.ref_pose, self.ref_vel
+        if tk["perturb_init_state_prob"] > 0.0:
+            perturb = m & (self._draw("u", 0.0 + (1.0 - 0.0) * u_perturb, m) < tk["perturb_init_state_prob"])
+            if np.any(perturb):
+                pose, vel = self._apply_state_perturb(pose, vel, perturb, z, axis)
         # _sync_sim_model :778-793 / _set_state :795-829
-        self.pos = np.where(mm, self.ref_pose[:, 0:3], self.pos)
-        self.quat = np.where(mm, self.ref_pose[:, 3:7], self.quat)
-        self.q = np.where(mm, self.ref_pose[:, 7:], self.q)
-        self.lin = np.where(mm, self.ref_vel[:, 0:3], self.lin)
-        self.ang = np.where(mm, self.ref_vel[:, 3:6], self.ang)
-        self.qd = np.where(mm, self.ref_vel[:, 6:], self.qd)
+        self.pos = np.where(mm, pose[:, 0:3], self.pos)
+        self.quat = np.where(mm, pose[:, 3:7], self.quat)
+        self.q = np.where(mm, pose[:, 7:], self.q)
+        self.lin = np.where(mm, vel[:, 0:3], self.lin)
+        self.ang = np.where(mm, vel[:, 3:6], self.ang)
+        self.qd = np.where(mm, vel[:, 6:], self.qd)
         self.receive_obs(m)
         return self.observation()
+
+    def _apply_state_perturb(self, pose, vel, mask, z, axis):
+        """imitation_task.py:1199-1243; z: 32 standard normals, axis: 3 uniforms in (-1, 1) per robot, consumed in the
+        reference's order (root xy, axis, angle, joint pose, root velocity xy, angular velocity, joint velocity)."""
+        root_pos_std, root_rot_std, joint_pose_std = 0.025, 0.025 * np.pi, 0.05 * np.pi
+        root_vel_std, root_ang_vel_std, joint_vel_std = 0.1, 0.05 * np.pi, 0.05 * np.pi
+        pose, vel = pose.copy(), vel.copy()
+        mm = mask[:, None]
+        dx = self._draw("n", root_pos_std * z[:, 0] + 0, mask)
+        dy = self._draw("n", root_pos_std * z[:, 1] + 0, mask)
+        ax = self._draw("u", axis, mask)
+        ax = ax / np.sqrt(np.sum(ax * ax, axis=-1, keepdims=True))
+        theta = self._draw("n", root_rot_std * z[:, 2] + 0, mask)
+        dj = self._draw("n", joint_pose_std * z[:, 3:15] + 0, mask)
+        dvx = self._draw("n", root_vel_std * z[:, 15] + 0, mask)
+        dvy = self._draw("n", root_vel_std * z[:, 16] + 0, mask)
+        dw = self._draw("n", root_ang_vel_std * z[:, 17:20] + 0, mask)
+        djv = self._draw("n", joint_vel_std * z[:, 20:32] + 0, mask)
+        p = pose[:, 0:3].copy(); p[:, 0] += dx; p[:, 1] += dy
+        rot = xf.quaternion_multiply(xf.quaternion_about_axis(theta, ax), pose[:, 3:7])
+        v = vel[:, 0:3].copy(); v[:, 0] += dvx; v[:, 1] += dvy
+        out_pose = np.concatenate([p, rot, pose[:, 7:] + dj], axis=-1)
+        out_vel = np.concatenate([v, vel[:, 3:6] + dw, vel[:, 6:] + djv], axis=-1)
+        return np.where(mm, out_pose, pose), np.where(mm, out_vel, vel)
 
     # ---- sensors (robot_sensors.py:74-84,153-190; environment_sensors.py:59-66) ------------
     def _sensor_readings(self):
@@ -315,6 +379,9 @@ class OracleEnv(object):
         dt = self.spec.action_repeat * self.spec.time_step          # quadruped_gym_env.py:177
         ref_base_pos = self.ref_pose[:, 0:3]
         heading = xf.calc_heading(self.get_base_orientation())
+        if self.task["tar_obs_noise"] is not None:                   # :274-275
+            zn = philox.tar_noise_draw(self.seed, self.gid, self.episode - 1, self.env_step_counter)
+            heading = heading + self._draw("n", self.task["tar_obs_noise"][0] * zn + 0, np.ones(self.N, dtype=bool))
         inv_rot = xf.quaternion_about_axis(-heading, [0, 0, 1])
         out = []
         for step in self.task["tar_frame_steps"]:
@@ -507,19 +574,35 @@ class OracleEnv(object):
         w = np.array([tk["pose_weight"], tk["velocity_weight"], tk["end_effector_weight"],
                       tk["root_pose_weight"], tk["root_velocity_weight"]])
         t = self.reward_terms()
-        return t[:, 0] * w[0] + t[:, 1] * w[1] + t[:, 2] * w[2] + t[:, 3] * w[3] + t[:, 4] * w[4]
+        return (t[:, 0] * w[0] + t[:, 1] * w[1] + t[:, 2] * w[2] + t[:, 3] * w[3] + t[:, 4] * w[4]) * tk["weight"]   # :350-356
 
     # ---- task update (imitation_task.py:201-207, 734-761, 1020-1055) -----------------------
     def update(self):
+        tk = self.task
         time = self.motion_time()
-        new_phase = self.lib.calc_phase(self.clip, time)
-        sync = self.task["enable_cycle_sync"] & (new_phase < self.prev_phase)
+        change = (time >= self.clip_change_time) & (self.lib.n_clips > 1)          # _check_change_clip :1096-1101
+        if np.any(change):                                                       # :742-746
+            clip_new, u_dur, u_off = philox.clip_change_draws(self.seed, self.gid, self.episode - 1, self.clip_changes, self.lib.n_clips)
+            self.clip = np.where(change, self._draw("i", clip_new, change), self.clip)
+            # _reset_clip_change_time reads the motion clock BEFORE the new time offset is drawn: still `time`
+            dur_v = self._draw("u", tk["clip_time_min"] + (tk["clip_time_max"] - tk["clip_time_min"]) * u_dur, change)
+            self.clip_change_time = np.where(change, time + dur_v, self.clip_change_time)
+            off = self._draw("u", 0 + (self.lib.duration[self.clip] - 0) * u_off, change)      # _sample_time_offset :1112-1123
+            self.time_offset = np.where(change, off, self.time_offset)
+            self.clip_changes = self.clip_changes + change
+        new_phase = self.lib.calc_phase(self.clip, time)            # :748-749: the NEW clip's phase at the OLD clock value
+        sync = (tk["enable_cycle_sync"] & (new_phase < self.prev_phase)) | change      # :751-754
         if np.any(sync):
-            ref = self.calc_ref_pose(time, apply_origin_offset=False)
+            time_s = self.motion_time()                             # _sync_ref_origin re-reads the clock (:1033)
+            ref = self.calc_ref_pose(time_s, apply_origin_offset=False)
+            if np.any(change):                                      # sync_root_rotation=change_clip :1037-1045
+                dh = self._heading_rel_default(self.quat) - self._heading_rel_default(ref[:, 3:7])
+                self.origin_rot = np.where(change[:, None], xf.quaternion_about_axis(dh, [0, 0, 1]), self.origin_rot)
             rp = xf.QuaternionRotatePoint(ref[:, 0:3], self.origin_rot)
             op = self.pos - rp
             op[:, 2] = 0
             self.origin_pos = np.where(sync[:, None], op, self.origin_pos)
+        time = self.motion_time()                                   # _update_ref_state :763-768
         self.ref_pose = self.calc_ref_pose(time)
         self.ref_vel = self.calc_ref_vel(time)
         self.prev_phase = new_phase
@@ -575,7 +658,7 @@ class OracleEnv(object):
                     "env_step_counter", "episode", "filt_x", "filt_y", "prev_filtered", "has_prev", "action",
                     "last_action", "hist", "hist_len", "ctrl_obs", "obs_torque", "imu_hist", "act_hist",
                     "ang_hist", "clip", "time_offset", "warmup", "origin_pos", "origin_rot", "prev_phase",
-                    "ref_pose", "ref_vel", "motor_strength")
+                    "ref_pose", "ref_vel", "motor_strength", "clip_change_time", "clip_changes")
 
     def get_state(self):
         return {k: np.array(getattr(self, k)) for k in self.STATE_FIELDS}

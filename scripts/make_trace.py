@@ -50,6 +50,72 @@ class DrawLog(object):
         np.random.uniform, np.random.randint = self._u, self._r
 
 
+class TaskDrawLog(object):
+    """Per-robot log of every draw an ImitationTask makes through its own helpers (_rand_uniform / _randint / _randn,
+    imitation_task.py:1125-1141), in call order: what oracle/env.py replays for the task options."""
+
+    def __init__(self, tasks):
+        self.logs = [[] for _ in tasks]
+        for log, t in zip(self.logs, tasks):
+            def wrap(kind, fn, log=log):
+                def f(*a, **kw):
+                    v = fn(*a, **kw)
+                    log.append((kind, np.array(v, dtype=np.float64)))
+                    return v
+                return f
+            t._rand_uniform = wrap("u", t._rand_uniform)
+            t._randint = wrap("i", t._randint)
+            t._randn = wrap("n", t._randn)
+
+    def flat(self):
+        """-> kinds (R, D) uint8 codes, values (R, D, 12) padded, counts (R,)"""
+        D = max(len(l) for l in self.logs)
+        kinds = np.zeros((len(self.logs), D), dtype=np.uint8)
+        vals = np.zeros((len(self.logs), D, 12))
+        size = np.zeros((len(self.logs), D), dtype=np.int64)
+        for r, l in enumerate(self.logs):
+            for d, (k, v) in enumerate(l):
+                kinds[r, d] = ord(k)
+                v = np.atleast_1d(v)
+                vals[r, d, :len(v)] = v
+                size[r, d] = len(v) if np.ndim(l[d][1]) else 0
+        return kinds, vals, size, np.array([len(l) for l in self.logs])
+
+
+def trace_options(reference, out, prefix, num_robot=4, steps=40):
+    """The task options run.py leaves off (clip switching, initial-state perturbation, target-observation noise) on the
+    reference's own classes: 3-clip Laikago library, clip timers of 0.2-0.5 s, perturbation probability 0.6."""
+    from envs.quadruped_robot.robots import minitaur
+    from envs.quadruped_robot.task import imitation_task
+    from envs.quadruped_robot import quadruped_gym_env, wrapper_env
+    names = ["laikago_pace", "laikago_trot", "laikago_spin"]
+    files = [os.path.join(reference, "OpenRoboRL/envs/quadruped_robot/task/motions", n + ".txt") for n in names]
+    robot = [minitaur.Minitaur(name_robot="laikago", robot_index=i, enable_randomizer=False) for i in range(num_robot)]
+    task = [imitation_task.ImitationTask(ref_motion_filenames=files, enable_cycle_sync=True, tar_frame_steps=[1, 2, 10, 30],
+                                         ref_state_init_prob=0.9, warmup_time=0.25, clip_time_min=0.2, clip_time_max=0.5,
+                                         perturb_init_state_prob=0.6, tar_obs_noise=[0.1, 0.2], weight=0.7) for _ in range(num_robot)]
+    genv = quadruped_gym_env.LocomotionGymEnv(robot, task)
+    env = wrapper_env.WrapperEnv(genv, episode_length_start=600, episode_length_end=600, curriculum_steps=30000000, num_parallel_envs=1)
+    np.random.seed(11)
+    log = TaskDrawLog(env.task)
+    obs = env.reset()
+    rng = np.random.RandomState(5)
+    O, R, D, A, TI = [np.array(obs)], [], [], [], []
+    for s in range(steps):
+        a = np.clip(rng.normal(scale=0.15, size=(num_robot, 12)), -2 * np.pi, 2 * np.pi)
+        A.append(a.copy())
+        obs, r, done, info = env.step([x.copy() for x in a])
+        O.append(np.array(obs)); R.append(np.array(r)); D.append(np.array(done))
+        TI.append(np.array([[t._get_motion_time(), t._prev_motion_phase] + list(t._origin_offset_pos) + list(t._origin_offset_rot)
+                            + [t._active_motion_id, t._clip_change_time, t._motion_time_offset] for t in env.task]))
+    kinds, vals, size, counts = log.flat()
+    out.update({prefix + "/draw_kind": kinds, prefix + "/draw_value": vals, prefix + "/draw_size": size, prefix + "/draw_count": counts,
+                prefix + "/obs": np.array(O), prefix + "/reward": np.array(R), prefix + "/done": np.array(D),
+                prefix + "/action": np.array(A), prefix + "/task": np.array(TI)})
+    changes = int(np.sum(np.diff(np.array(TI)[..., 9], axis=0) != 0))
+    print("%s: %d draws per robot %s, %d clip changes, rewards %.3f..%.3f" % (prefix, kinds.shape[1], counts, changes, np.min(R), np.max(R)))
+
+
 def trace(reference, robot_name, clip_name, policy_name, num_robot, steps, want_warmup, out, prefix):
     from tests import common
     mfile = os.path.join(reference, "OpenRoboRL/envs/quadruped_robot/task/motions", clip_name + ".txt")
@@ -97,6 +163,9 @@ def main(reference, gold):
     trace(reference, "mini_cheetah", "minicheetah_trot", "minicheetah_trot", 2, 18, False, out, "minicheetah_trot")
     np.savez_compressed(os.path.join(gold, "ref_task_trace.npz"), **out)
     print("ref_task_trace.npz:", len(out), "arrays")
+    opt = {}
+    trace_options(reference, opt, "laikago_options")
+    np.savez_compressed(os.path.join(gold, "ref_task_options_trace.npz"), **opt)
 
 
 if __name__ == "__main__":
