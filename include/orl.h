@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define ORL_ABI_VERSION 2
+#define ORL_ABI_VERSION 3
 #define ORL_NUM_LEGS 4
 #define ORL_LEG_DOF 3
 #define ORL_NUM_MOTORS 12
@@ -88,6 +88,15 @@ typedef struct {
   float rand_lo[8], rand_hi[8];
   float joint_friction_k;       /* slope of the regularised Coulomb joint friction, N m s / rad (this repo's model) */
   float mu_plane;               /* lateral friction of the ground plane (combined with the randomised foot friction) */
+  /* Task options R/run.py leaves at their defaults (imitation_task.py:36-57).  Any non-default value selects the
+   * option instantiation of the step / reset kernels; the defaults run the same code as ABI 2. */
+  float reward_weight;          /* `weight`: reward() returns reward * weight (:104, 356); 1 */
+  int32_t enable_rand_init_time;/* 0: every episode starts at motion time offset 0 (:1103-1106); 1 */
+  double clip_time_min, clip_time_max; /* clip switching: a new clip after U(min, max) seconds of motion time
+                                   (:1057-1101, 740-754); INFINITY (either) = off */
+  double perturb_init_state_prob; /* probability of a perturbed start state (:192-195, 1199-1243); 0 */
+  int32_t enable_tar_obs_noise; /* tar_obs_noise is not None (:274-275) */
+  float tar_obs_noise;          /* tar_obs_noise[0]: std of the heading noise of the target observation */
 } orl_config;
 
 enum { ORL_RAND_BATTERY = 0, ORL_RAND_INERTIA = 1, ORL_RAND_JOINT_FRICTION = 2, ORL_RAND_LATENCY = 3,
@@ -155,7 +164,9 @@ typedef struct {
   int32_t ep_return;
   int32_t obs_quat;
   int32_t motor_strength;
-  int32_t rand_params;          /* 12: base/leg mass ratio, base/leg inertia ratio, latency, foot friction x plane (-1: model), knee friction[4], pad */
+  int32_t rand_params;          /* 10: base/leg mass ratio, base/leg inertia ratio, latency, foot friction x plane (-1: model), knee friction[4] */
+  int32_t clip_change_time;     /* f64 (2 floats): motion time of the next clip change (imitation_task.py:123, 1057-1067; +inf: none) */
+  int32_t clip_changes;         /* i32: clip changes of the running episode (RNG counter) */
 } orl_state_layout;
 
 /* ---- lifetime -------------------------------------------------------------------------------- */
@@ -223,6 +234,20 @@ int orl_fk(orl_env* env, const float* pose_dev, int32_t n, float* com_dev, void*
 #define ORL_LAT_RING 42
 int orl_get_latency_rings_host(orl_env* env, float* ring_q, float* ring_b);
 int orl_set_latency_rings_host(orl_env* env, const float* ring_q, const float* ring_b);
+/* MotorModel.convert_to_torque (R/envs/quadruped_robot/robots/minitaur_motor.py:104-173) for n robots, all three
+ * control modes.  The env path itself is POSITION only, as in the reference (minitaur.py:113 hard-codes it and
+ * Minitaur.step never passes another mode); this entry point serves callers of the motor model.
+ *   mode ORL_MOTOR_POSITION: commands [n][12] desired motor angles
+ *        ORL_MOTOR_TORQUE  : commands [n][12] torques (scaled by the strength ratios, no clipping: :137-140)
+ *        ORL_MOTOR_HYBRID  : commands [n][60], per motor (position, kp, velocity, kd, torque) (:153-162, 25-31)
+ * motor_angle / motor_velocity [n][12] in motor space; kp / kd [12] (ignored in HYBRID / TORQUE); strength [n][12] or NULL
+ * (= 1); torque_limits [12] or NULL (no clipping, :167-171).  All pointers are device pointers.  out [n][12]. */
+enum { ORL_MOTOR_POSITION = 1, ORL_MOTOR_TORQUE = 2, ORL_MOTOR_HYBRID = 3 };
+int orl_motor_convert_to_torque(int32_t mode, const float* commands_dev, const float* motor_angle_dev,
+                                const float* motor_velocity_dev, const float* kp_dev, const float* kd_dev,
+                                const float* strength_dev, const float* torque_limits_dev, int32_t n,
+                                float* out_dev, void* stream);
+
 /* Randomizer values [n][12] (layout of orl_state_layout.rand_params) used by the three dynamics entry points below;
  * NULL (default) = the model's own masses, inertias and friction. */
 int orl_set_dynamics_rand(orl_env* env, const float* rand_dev);

@@ -6,11 +6,12 @@ There is deliberately no fallback: if `csrc/libopenroborl_b200.so` has not been 
 import ctypes as C
 import os
 
-ORL_ABI_VERSION = 2
+ORL_ABI_VERSION = 3
 NUM_LEGS, LEG_DOF, NUM_MOTORS = 4, 3, 12
 POSE_SIZE, VEL_SIZE, OBS_SIZE, NUM_TAR_FRAMES = 19, 18, 160, 4
 MAX_CP, MAX_LINKS, CYCLE_TABLE = 24, 32, 128
 
+MOTOR_POSITION, MOTOR_TORQUE, MOTOR_HYBRID = 1, 2, 3
 ORL_OK, ORL_ERR_INVALID, ORL_ERR_CUDA, ORL_ERR_STATE, ORL_ERR_ASSERT = 0, -1, -2, -3, -4
 
 
@@ -35,6 +36,9 @@ class OrlConfig(C.Structure):
         ("max_coordinate_velocity", C.c_float),
         ("enable_randomizer", C.c_int32), ("rand_lo", C.c_float * 8), ("rand_hi", C.c_float * 8),
         ("joint_friction_k", C.c_float), ("mu_plane", C.c_float),
+        ("reward_weight", C.c_float), ("enable_rand_init_time", C.c_int32),
+        ("clip_time_min", C.c_double), ("clip_time_max", C.c_double), ("perturb_init_state_prob", C.c_double),
+        ("enable_tar_obs_noise", C.c_int32), ("tar_obs_noise", C.c_float),
     ]
 
 
@@ -72,7 +76,7 @@ class OrlStateLayout(C.Structure):
         "stride", "pos", "quat", "q", "lin", "ang", "qd", "filt_x", "filt_y", "prev_filtered", "ring1", "ring2",
         "imu_hist", "act_hist", "ang_hist", "ref_pose", "ref_vel", "origin_pos", "origin_rot", "time_offset",
         "prev_phase", "clip", "warmup", "substep_counter", "step_counter", "env_step_counter", "episode",
-        "ep_return", "obs_quat", "motor_strength", "rand_params")]
+        "ep_return", "obs_quat", "motor_strength", "rand_params", "clip_change_time", "clip_changes")]
 
 
 # every symbol include/orl.h declares: name -> (restype, argtypes)
@@ -106,6 +110,7 @@ SYMBOLS = {
     "orl_reward_terms": (C.c_int, [_P, _P, _P]),
     "orl_launch_count": (C.c_int64, [_P]),
     "orl_fp32_peak": (C.c_int, [C.c_int32, C.c_int32, _P]),
+    "orl_motor_convert_to_torque": (C.c_int, [C.c_int32, _P, _P, _P, _P, _P, _P, _P, C.c_int32, _P, _P]),
     "orl_gae": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_int32, C.c_int32, _P, _P, _P]),
 }
 

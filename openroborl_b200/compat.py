@@ -14,6 +14,8 @@ All arithmetic of reset()/step() runs in the fused CUDA kernels through the C AB
 points orl_reset_host / orl_step_host); these classes only adapt lists <-> arrays.  Per-object methods
 of the reference that assume one Python object per robot stepping one Bullet world (Minitaur.robot_step,
 ImitationTask.update, ...) have no meaning in a fused batched step and raise NotImplementedError.
+Every constructor option of the reference's ImitationTask is accepted (clip switching, initial-state perturbation,
+target-observation noise, weight, enable_rand_init_time: the option instantiation of the kernels).
 """
 import math
 
@@ -160,11 +162,8 @@ class ImitationTask(object):
                  root_pose_err_scale=20, root_velocity_err_scale=2, perturb_init_state_prob=0.0, tar_obs_noise=None,
                  draw_ref_model_alpha=0.5):
         assert ref_motion_filenames is not None                                    # imitation_task.py:109
-        if np.isfinite(clip_time_min) or np.isfinite(clip_time_max):
-            raise NotImplementedError("clip switching (finite clip_time_min/max) is not built; run.py never enables it")
-        if perturb_init_state_prob > 0 or tar_obs_noise is not None or not enable_rand_init_time or weight != 1.0 \
-                or clip_velocity is not None:
-            raise NotImplementedError("option not used by run.py and not built on the CUDA path")
+        # clip_velocity is stored and never read by the reference either (imitation_task.py:106)
+        self._clip_velocity = clip_velocity
         self._ref_motion_filenames = ref_motion_filenames
         self._tar_frame_steps = [1, 2] if tar_frame_steps is None else list(tar_frame_steps)   # :118-119
         self.params = dict(
@@ -173,7 +172,11 @@ class ImitationTask(object):
             velocity_weight=velocity_weight, end_effector_weight=end_effector_weight, root_pose_weight=root_pose_weight,
             root_velocity_weight=root_velocity_weight, pose_err_scale=pose_err_scale, velocity_err_scale=velocity_err_scale,
             end_effector_err_scale=end_effector_err_scale, end_effector_height_err_scale=end_effector_height_err_scale,
-            root_pose_err_scale=root_pose_err_scale, root_velocity_err_scale=root_velocity_err_scale)
+            root_pose_err_scale=root_pose_err_scale, root_velocity_err_scale=root_velocity_err_scale,
+            # options run.py leaves off: the option instantiation of the CUDA kernels (orl.h "task options")
+            weight=float(weight), enable_rand_init_time=bool(enable_rand_init_time), clip_time_min=float(clip_time_min),
+            clip_time_max=float(clip_time_max), perturb_init_state_prob=float(perturb_init_state_prob),
+            tar_obs_noise=None if tar_obs_noise is None else tuple(float(v) for v in tar_obs_noise))
         self._env, self._index = None, 0
 
     def _bind(self, env, index):
@@ -204,7 +207,7 @@ class ImitationTask(object):
         p = self.params
         t = self._env._cuda.reward_terms()[self._index].astype(np.float64)
         return float(p["pose_weight"] * t[0] + p["velocity_weight"] * t[1] + p["end_effector_weight"] * t[2]
-                     + p["root_pose_weight"] * t[3] + p["root_velocity_weight"] * t[4])
+                     + p["root_pose_weight"] * t[3] + p["root_velocity_weight"] * t[4]) * p["weight"]      # :356
 
     cal_reward = reward
 

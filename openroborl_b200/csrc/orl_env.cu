@@ -4,6 +4,7 @@
 // across the boundary.
 #include <cuda_runtime.h>
 #include <math.h>
+#include <cmath>
 #include <stdio.h>
 #include <stdlib.h>
 #include <stdarg.h>
@@ -28,6 +29,7 @@ struct orl_env {
   float* d_state;
   float* d_next_ep; int* d_prepared; int* d_todo; int* d_todo_count;   // episodes prepared ahead of time (auto-reset only)
   int prep_parity; bool prep_scan;
+  bool opt;                        // a task option of ABI 3 is on: the OPT instantiations of the step / reset kernels run
   DevModel* d_model;
   double* d_stats;
   std::vector<void*> d_motion;     // owned motion-table buffers
@@ -116,6 +118,11 @@ static void fill_dev_cfg(orl_env* e) {
   d.randomize = c.enable_randomizer;
   d.mu_plane = c.mu_plane;
   for (int i = 0; i < 8; ++i) { d.rand_lo[i] = c.rand_lo[i]; d.rand_hi[i] = c.rand_hi[i]; }
+  d.reward_weight = c.reward_weight; d.rand_init_time = c.enable_rand_init_time;
+  d.clip_tmin = c.clip_time_min; d.clip_tmax = c.clip_time_max; d.perturb_prob = c.perturb_init_state_prob;
+  d.tar_noise_on = c.enable_tar_obs_noise; d.tar_noise = c.tar_obs_noise;
+  e->opt = c.reward_weight != 1.0f || !c.enable_rand_init_time || (std::isfinite(c.clip_time_min) && std::isfinite(c.clip_time_max)) ||
+           c.perturb_init_state_prob > 0.0 || c.enable_tar_obs_noise;
 }
 
 static float f_from_i(int32_t i) { float f; memcpy(&f, &i, 4); return f; }
@@ -247,6 +254,10 @@ extern "C" int orl_create(const orl_config* cfg, const orl_robot_model* model, o
   }
   if (!(cfg->contact_d0 > 0) || !(cfg->limit_e0 > 0)) return fail(e, ORL_ERR_INVALID, "contact_d0 and limit_e0 must be positive");
   if (!(cfg->max_coordinate_velocity > 0)) return fail(e, ORL_ERR_INVALID, "max_coordinate_velocity must be positive");
+  if (std::isfinite(cfg->clip_time_min) && std::isfinite(cfg->clip_time_max) && !(cfg->clip_time_max >= cfg->clip_time_min && cfg->clip_time_min >= 0.0))
+    return fail(e, ORL_ERR_INVALID, "clip_time_min / clip_time_max must satisfy 0 <= min <= max");
+  if (cfg->clip_time_min != cfg->clip_time_min || cfg->clip_time_max != cfg->clip_time_max || !(cfg->perturb_init_state_prob >= 0.0))
+    return fail(e, ORL_ERR_INVALID, "bad task option (NaN clip time or negative perturbation probability)");
   if (cfg->enable_randomizer) {
     for (int i = 0; i < 8; ++i)
       if (!(cfg->rand_hi[i] >= cfg->rand_lo[i])) return fail(e, ORL_ERR_INVALID, "randomizer range %d is empty", i);
@@ -279,6 +290,8 @@ extern "C" int orl_create(const orl_config* cfg, const orl_robot_model* model, o
       for (int m = 0; m < 12; ++m) S[S_STRENGTH + m] = 1.f;
       S[S_OBSQ + 3] = 1.f; S[S_OROT + 3] = 1.f; S[S_QUAT + 3] = 1.f;
       S[S_RAND + 0] = S[S_RAND + 1] = S[S_RAND + 2] = S[S_RAND + 3] = 1.f; S[S_RAND + 5] = -1.f;
+      const double never = INFINITY;
+      memcpy(S + S_CHANGET, &never, sizeof(double));
     }
     CUDA_TRY(e, cudaMemcpy(e->d_state, init.data(), nstate * sizeof(float), cudaMemcpyHostToDevice));
   }
@@ -295,9 +308,12 @@ extern "C" int orl_create(const orl_config* cfg, const orl_robot_model* model, o
   CUDA_TRY(e, cudaMalloc(&e->d_mask, (size_t)N));
   CUDA_TRY(e, cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   for (int i = 0; i < ORL_D2H_CHUNKS; ++i) CUDA_TRY(e, cudaEventCreateWithFlags(&e->ev_chunk[i], cudaEventDisableTiming));
-  CUDA_TRY(e, cudaFuncSetAttribute(orl_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ORL_SMEM_BYTES));
-  CUDA_TRY(e, cudaFuncSetAttribute(orl_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ORL_SMEM_BYTES));
-  CUDA_TRY(e, cudaFuncSetAttribute(orl_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ORL_SMEM_BYTES));
+  CUDA_TRY(e, cudaFuncSetAttribute(orl_step_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ORL_SMEM_BYTES));
+  CUDA_TRY(e, cudaFuncSetAttribute(orl_step_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ORL_SMEM_BYTES));
+  CUDA_TRY(e, cudaFuncSetAttribute(orl_step_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ORL_SMEM_BYTES));
+  CUDA_TRY(e, cudaFuncSetAttribute(orl_step_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ORL_SMEM_BYTES));
+  CUDA_TRY(e, cudaFuncSetAttribute(orl_reset_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ORL_SMEM_BYTES));
+  CUDA_TRY(e, cudaFuncSetAttribute(orl_reset_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ORL_SMEM_BYTES));
   e->dev.state = e->d_state; e->dev.model = e->d_model; e->dev.stats = e->d_stats;
   e->dev.ring_q = nullptr; e->dev.ring_b = nullptr;
   e->dev.next_ep = nullptr; e->dev.prepared = nullptr; e->dev.prep_blocks = 0;
@@ -502,7 +518,8 @@ extern "C" int orl_reset(orl_env* e, const uint8_t* mask_dev, float* obs_dev, vo
   if ((uintptr_t)obs_dev & 15) return fail(e, ORL_ERR_INVALID, "observation buffer must be 16-byte aligned");
   DevEnv d = e->dev;
   d.prep_parity = e->prep_parity ^ 1;          // queue_for_preparation appends to list prep_parity ^ 1 = the one the next step launch reads
-  orl_reset_kernel<<<blocks, ORL_BLOCK_THREADS, ORL_SMEM_BYTES, (cudaStream_t)stream>>>(d, mask_dev, obs_dev);
+  if (e->opt) orl_reset_kernel<true><<<blocks, ORL_BLOCK_THREADS, ORL_SMEM_BYTES, (cudaStream_t)stream>>>(d, mask_dev, obs_dev);
+  else orl_reset_kernel<false><<<blocks, ORL_BLOCK_THREADS, ORL_SMEM_BYTES, (cudaStream_t)stream>>>(d, mask_dev, obs_dev);
   return check_launch(e, "orl_reset_kernel");
 }
 
@@ -524,8 +541,15 @@ static int step_launch(orl_env* e, const float* actions_dev, float* obs_dev, flo
   d.prep_parity = e->prep_parity; d.prep_scan = e->prep_scan ? 1 : 0;
   d.obs_split = obs_split ? 1 : 0;
   e->prep_parity ^= 1; e->prep_scan = false;
-  if (e->dev.ring_q) orl_step_kernel<true><<<blocks + d.prep_blocks, ORL_BLOCK_THREADS, ORL_SMEM_BYTES, (cudaStream_t)stream>>>(d, actions_dev, obs_dev, reward_dev, done_dev);
-  else orl_step_kernel<false><<<blocks + d.prep_blocks, ORL_BLOCK_THREADS, ORL_SMEM_BYTES, (cudaStream_t)stream>>>(d, actions_dev, obs_dev, reward_dev, done_dev);
+  const dim3 grid(blocks + d.prep_blocks);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (e->opt) {
+    if (e->dev.ring_q) orl_step_kernel<true, true><<<grid, ORL_BLOCK_THREADS, ORL_SMEM_BYTES, st>>>(d, actions_dev, obs_dev, reward_dev, done_dev);
+    else orl_step_kernel<false, true><<<grid, ORL_BLOCK_THREADS, ORL_SMEM_BYTES, st>>>(d, actions_dev, obs_dev, reward_dev, done_dev);
+  } else {
+    if (e->dev.ring_q) orl_step_kernel<true, false><<<grid, ORL_BLOCK_THREADS, ORL_SMEM_BYTES, st>>>(d, actions_dev, obs_dev, reward_dev, done_dev);
+    else orl_step_kernel<false, false><<<grid, ORL_BLOCK_THREADS, ORL_SMEM_BYTES, st>>>(d, actions_dev, obs_dev, reward_dev, done_dev);
+  }
   return check_launch(e, "orl_step_kernel");
 }
 
@@ -659,6 +683,7 @@ extern "C" int orl_state_layout_get(const orl_env* e, orl_state_layout* o) {
   o->env_step_counter = S_ENVSTEP; o->episode = S_EPISODE; o->ep_return = S_EPRET; o->obs_quat = S_OBSQ;
   o->motor_strength = S_STRENGTH;
   o->rand_params = S_RAND;
+  o->clip_change_time = S_CHANGET; o->clip_changes = S_NCHANGE;
   return ORL_OK;
 }
 
@@ -845,6 +870,41 @@ __global__ void orl_gae_kernel(const float* __restrict__ rew, const float* __res
     const float m = (float)mean, inv = var > 0.0 ? (float)(1.0 / sqrt(var)) : 1.0f;
     for (int t = 0; t < T; ++t) { const long idx = (long)t * N + i; adv[idx] = (adv[idx] - m) * inv; }
   }
+}
+
+// MotorModel.convert_to_torque (minitaur_motor.py:104-173): one thread per (robot, motor)
+__global__ void orl_motor_kernel(int mode, const float* __restrict__ cmd, const float* __restrict__ q, const float* __restrict__ qd,
+                                 const float* __restrict__ kp, const float* __restrict__ kd, const float* __restrict__ strength,
+                                 const float* __restrict__ limits, int n, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * ORL_NUM_MOTORS) return;
+  const int r = i / ORL_NUM_MOTORS, m = i - r * ORL_NUM_MOTORS;
+  const float sr = strength ? strength[i] : 1.0f;
+  if (mode == ORL_MOTOR_TORQUE) { out[i] = sr * cmd[i]; return; }                       // :137-140 (no clipping)
+  float p, d, des_q, des_qd, add;
+  if (mode == ORL_MOTOR_POSITION) { p = kp[m]; d = kd[m]; des_q = cmd[i]; des_qd = 0.f; add = 0.f; }   // :147-152
+  else {                                                                                 // HYBRID :153-162
+    const float* c = cmd + (size_t)r * (5 * ORL_NUM_MOTORS) + 5 * m;
+    des_q = c[0]; p = c[1]; des_qd = c[2]; d = c[3]; add = c[4];
+  }
+  float t = -1.0f * (p * (q[i] - des_q)) - d * (qd[i] - des_qd) + add;                   // :163-165
+  t = sr * t;
+  if (limits) t = fminf(fmaxf(t, -1.0f * limits[m]), limits[m]);                         // :167-171
+  out[i] = t;
+}
+
+extern "C" int orl_motor_convert_to_torque(int32_t mode, const float* commands_dev, const float* motor_angle_dev,
+                                           const float* motor_velocity_dev, const float* kp_dev, const float* kd_dev,
+                                           const float* strength_dev, const float* torque_limits_dev, int32_t n,
+                                           float* out_dev, void* stream) {
+  if (mode != ORL_MOTOR_POSITION && mode != ORL_MOTOR_TORQUE && mode != ORL_MOTOR_HYBRID) return ORL_ERR_INVALID;   // PWM: ValueError, :133-135
+  if (n <= 0 || !commands_dev || !out_dev) return ORL_ERR_INVALID;
+  if (mode != ORL_MOTOR_TORQUE && (!motor_angle_dev || !motor_velocity_dev)) return ORL_ERR_INVALID;
+  if (mode == ORL_MOTOR_POSITION && (!kp_dev || !kd_dev)) return ORL_ERR_INVALID;
+  const int total = n * ORL_NUM_MOTORS;
+  orl_motor_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(mode, commands_dev, motor_angle_dev, motor_velocity_dev,
+                                                                         kp_dev, kd_dev, strength_dev, torque_limits_dev, n, out_dev);
+  return cudaGetLastError() == cudaSuccess ? ORL_OK : ORL_ERR_CUDA;
 }
 
 extern "C" int orl_gae(const float* rewards_dev, const float* vpred_dev, const float* nextvpred_dev, const uint8_t* episode_starts_dev,

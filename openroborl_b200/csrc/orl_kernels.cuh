@@ -29,6 +29,11 @@ struct DevCfg {
   int randomize;                   // domain randomizer on reset (minitaur.py:273-276)
   float mu_plane;
   float rand_lo[8], rand_hi[8];    // ranges in the reference's sorted parameter order (ORL_RAND_*)
+  // Task options run.py leaves off (imitation_task.py:36-57): only read by the OPT instantiations of the kernels
+  float reward_weight;
+  int rand_init_time;
+  double clip_tmin, clip_tmax, perturb_prob;
+  int tar_noise_on; float tar_noise;
 };
 
 struct DevEnv {
@@ -184,9 +189,31 @@ ORL_DI double motion_time(float* S, const DevCfg& C) {
 }
 ORL_DI Q4 ldq4(float4 v) { return q4(v.x, v.y, v.z, v.w); }
 
+// ---- random draws of the task options: further blocks of the (robot, episode) Philox stream (oracle/philox.py) ------
+#define ORL_OPT_BLOCK 9u
+#define ORL_NORMAL_BLOCK0 10u
+#define ORL_AXIS_BLOCK 26u
+#define ORL_CHANGE_BLOCK0 32u
+#define ORL_NOISE_BLOCK0 0x40000000u
+ORL_DI void opt_block(const DevCfg& C, int gid, int episode, uint32_t ctr, uint32_t w[4]) {
+  philox4x32((uint32_t)gid, (uint32_t)episode, ctr, 0u, (uint32_t)(C.seed & 0xffffffffull), (uint32_t)(C.seed >> 32), w);
+}
+ORL_DI double u01_32(uint32_t w) { return ((double)w + 0.5) * (1.0 / 4294967296.0); }
+// Box-Muller in FP64 (rare paths only): sqrt(-2 ln u1) cos(2 pi u2)
+ORL_DI double normal_f64(uint32_t w0, uint32_t w1) {
+  return sqrt(-2.0 * log(u01_32(w0))) * cos(2.0 * 3.141592653589793 * u01_32(w1));
+}
+// standard normal number i of the initial-state perturbation of (robot, episode)
+ORL_DI double perturb_normal(const DevCfg& C, int gid, int episode, int i) {
+  uint32_t w[4];
+  opt_block(C, gid, episode, ORL_NORMAL_BLOCK0 + (uint32_t)(i >> 1), w);
+  return (i & 1) ? normal_f64(w[2], w[3]) : normal_f64(w[0], w[1]);
+}
+
 // Observation rows: sensor histories (already in the record) + the target frames.
 // ImitationTask.build_target_obs (imitation_task.py:254-301): lane j of the quad builds frame j.
-ORL_DI void build_obs(float* S, float* O, const DevEnv& E, int leg) {
+template <bool OPT>
+ORL_DI void build_obs(float* S, float* O, const DevEnv& E, int leg, int gid) {
   const DevCfg& C = E.cfg;
   static_assert(S_IMU % 4 == 0 && ORL_STRIDE % 4 == 0 && ORL_OBS_SIZE % 4 == 0, "history block must be float4 aligned");
 #pragma unroll 1
@@ -207,6 +234,15 @@ ORL_DI void build_obs(float* S, float* O, const DevEnv& E, int leg) {
     bullet_euler(oq, roll, pitch, yaw);
     qheading_neg_sincos(bullet_quat_from_euler(roll, pitch, yaw), sh, ch);
   }
+  if (OPT && C.tar_noise_on) {                // heading += randn(0, tar_obs_noise[0]) (imitation_task.py:274-275)
+    uint32_t w[4];
+    opt_block(C, gid, as_int(S[S_EPISODE]) - 1, ORL_NOISE_BLOCK0 + (uint32_t)as_int(S[S_ENVSTEP]), w);
+    const double nz = (double)C.tar_noise * normal_f64(w[0], w[1]) + 0.0;
+    float sn, cn;
+    sincos_f64arg(nz, sn, cn);                // (sh, ch) = sin / cos of -heading: rotate by -noise
+    const float s2 = sh * cn - ch * sn, c2 = ch * cn + sh * sn;
+    sh = s2; ch = c2;
+  }
   half_angle(sh, ch, shh, chh);
   const Q4 inv_rot = q4(0.f, 0.f, shh, chh);
   const double tt = __dadd_rn(t0, __dmul_rn((double)C.tar_steps[leg], C.env_dt));
@@ -224,6 +260,7 @@ ORL_DI void build_obs(float* S, float* O, const DevEnv& E, int leg) {
 // Episode reset of one robot, executed by its quad on the staged record.
 // Minitaur.reset (minitaur.py:232-278) + ImitationTask.reset/_reset_ref_motion/_sync_sim_model
 // (imitation_task.py:166-199, 694-732, 778-793).  `qmask` = the 4 lanes of this quad.
+template <bool OPT>
 ORL_DI void reset_robot(float* S, const DevEnv& E, const DevModel& Mo, int gid, int leg, unsigned qmask) {
   const DevCfg& C = E.cfg;
   const DevLeg& L = Mo.leg[leg];
@@ -236,8 +273,9 @@ ORL_DI void reset_robot(float* S, const DevEnv& E, const DevModel& Mo, int gid, 
   const double u_time = u01_53(rb[0], rb[1]);
   const bool ref_init = u_rsi < C.rsi_prob;                          // imitation_task.py:183-184
   const bool warm = !ref_init && C.warmup_time > 0.0;                 // :186-188
-  const double toff = warm ? __dadd_rn(0.0, __dmul_rn(__dsub_rn(C.warmup_time, 0.0), u_time))
-                           : __dadd_rn(0.0, __dmul_rn(__dsub_rn(E.mt.dur[clip], 0.0), u_time));   // :1103-1123
+  double toff = warm ? __dadd_rn(0.0, __dmul_rn(__dsub_rn(C.warmup_time, 0.0), u_time))
+                     : __dadd_rn(0.0, __dmul_rn(__dsub_rn(E.mt.dur[clip], 0.0), u_time));   // :1103-1123
+  if (OPT && !C.rand_init_time) toff = 0.0;                          // :1104-1105
   __syncwarp(qmask);
   // per-motor fields owned by this lane
 #pragma unroll
@@ -319,15 +357,54 @@ ORL_DI void reset_robot(float* S, const DevEnv& E, const DevModel& Mo, int gid, 
     st3(S + S_REFPOSE, rp); stq(S + S_REFPOSE + 3, rq);
     st3(S + S_REFVEL, rl); st3(S + S_REFVEL + 3, ra3);
     st_f64(S + S_PPHASE, motion_phase(E.mt, clip, time));
+  }
+  // options: clip timer (_reset_clip_change_time, :1057-1067, last call of _reset_ref_motion) and the perturbed start
+  // state (:192-195, 1199-1243) -- the reference pose / velocity stay unperturbed, only what _sync_sim_model sets moves
+  bool perturb = false;
+  if (OPT) {
+    uint32_t w[4];
+    opt_block(C, gid, episode, ORL_OPT_BLOCK, w);
+    const double u_perturb = u01_53(w[0], w[1]), u_dur = u01_53(w[2], w[3]);
+    const bool switching = isfinite(C.clip_tmin) && isfinite(C.clip_tmax);
+    const double change_t = switching ? __dadd_rn(time, __dadd_rn(C.clip_tmin, __dmul_rn(__dsub_rn(C.clip_tmax, C.clip_tmin), u_dur)))
+                                      : (double)INFINITY;
+    if (leg == 0) { st_f64(S + S_CHANGET, change_t); as_int(S[S_NCHANGE]) = 0; }
+    perturb = C.perturb_prob > 0.0 && __dadd_rn(0.0, __dmul_rn(1.0, u_perturb)) < C.perturb_prob;
+  }
+  if (leg == 0) {
+    float3 sp = rp, sl = rl, sa = ra3; Q4 sq = rq;
+    if (OPT && perturb) {
+      const double pi = 3.141592653589793;
+      sp.x = (float)((double)sp.x + (0.025 * perturb_normal(C, gid, episode, 0) + 0.0));
+      sp.y = (float)((double)sp.y + (0.025 * perturb_normal(C, gid, episode, 1) + 0.0));
+      uint32_t wa[4];
+      opt_block(C, gid, episode, ORL_AXIS_BLOCK, wa);
+      double ax = -1.0 + 2.0 * u01_32(wa[0]), ay = -1.0 + 2.0 * u01_32(wa[1]), az = -1.0 + 2.0 * u01_32(wa[2]);
+      const double inv = 1.0 / sqrt(ax * ax + ay * ay + az * az);
+      const double th = 0.025 * pi * perturb_normal(C, gid, episode, 2) + 0.0;
+      const double sh = sin(0.5 * th), ch = cos(0.5 * th);
+      sq = qmul(q4((float)(ax * inv * sh), (float)(ay * inv * sh), (float)(az * inv * sh), (float)ch), rq);
+      sl.x = (float)((double)sl.x + (0.1 * perturb_normal(C, gid, episode, 15) + 0.0));
+      sl.y = (float)((double)sl.y + (0.1 * perturb_normal(C, gid, episode, 16) + 0.0));
+      sa.x = (float)((double)sa.x + (0.05 * pi * perturb_normal(C, gid, episode, 17) + 0.0));
+      sa.y = (float)((double)sa.y + (0.05 * pi * perturb_normal(C, gid, episode, 18) + 0.0));
+      sa.z = (float)((double)sa.z + (0.05 * pi * perturb_normal(C, gid, episode, 19) + 0.0));
+    }
     // _sync_sim_model
-    st3(S + S_POS, rp); stq(S + S_QUAT, rq); st3(S + S_LIN, rl); st3(S + S_ANG, ra3);
+    st3(S + S_POS, sp); stq(S + S_QUAT, sq); st3(S + S_LIN, sl); st3(S + S_ANG, sa);
   }
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     const int j = 3 * leg + k;
     const float qj = ref_joint(E.mt, F, s, j), vj = ref_joint_vel(E.mt, F, s, j);
     S[S_REFPOSE + 7 + j] = qj; S[S_REFVEL + 6 + j] = vj;
-    S[S_Q + j] = qj; S[S_QD + j] = vj;
+    float sqj = qj, svj = vj;
+    if (OPT && perturb) {
+      const double pi = 3.141592653589793;
+      sqj = (float)((double)qj + (0.05 * pi * perturb_normal(C, gid, episode, 3 + j) + 0.0));
+      svj = (float)((double)vj + (0.05 * pi * perturb_normal(C, gid, episode, 20 + j) + 0.0));
+    }
+    S[S_Q + j] = sqj; S[S_QD + j] = svj;
   }
   __syncwarp(qmask);
 }
@@ -373,6 +450,7 @@ ORL_DI void queue_for_preparation(const DevEnv& E, int robot) {
   if (slot < 2 * E.cfg.n) E.todo[(size_t)list * 2 * E.cfg.n + slot] = robot;
 }
 // The whole in-kernel reset of one robot: from the prepared record when it is there, else computed on the spot.
+template <bool OPT>
 ORL_DI void finish_episode(float* S, const DevEnv& E, const DevModel& Mo, int robot_c, int leg, unsigned qmask, bool valid) {
   bool ready = false;
   if (E.next_ep) {
@@ -394,7 +472,7 @@ ORL_DI void finish_episode(float* S, const DevEnv& E, const DevModel& Mo, int ro
     for (int k = 0; k < kPerLane; ++k) { const int i = leg + 4 * k; if (i < ORL_STRIDE / 4) dst[i] = v[k]; }
     __syncwarp(qmask);
   } else {
-    reset_robot(S, E, Mo, E.cfg.gid0 + robot_c, leg, qmask);
+    reset_robot<OPT>(S, E, Mo, E.cfg.gid0 + robot_c, leg, qmask);
   }
   reset_rings(S, E, Mo, E.cfg.gid0 + robot_c, leg, qmask, valid);
   if (valid && leg == 0) queue_for_preparation(E, robot_c);
@@ -405,6 +483,7 @@ ORL_DI void finish_episode(float* S, const DevEnv& E, const DevModel& Mo, int ro
 // Thread blocks [0, prep_blocks) of a step launch: one quad per queued robot (or, in scan mode, per robot of the batch
 // whose record is missing) writes the record of that robot's next episode.  Scratch records and a copy of the model
 // live in shared memory like in the worker blocks.
+template <bool OPT>
 ORL_DI void prepare_episodes(const DevEnv& E, unsigned char* smem) {
   const int lane = threadIdx.x & 31, leg = lane & 3, rw = lane >> 2, warp = threadIdx.x >> 5;
   {
@@ -444,7 +523,7 @@ ORL_DI void prepare_episodes(const DevEnv& E, unsigned char* smem) {
       __syncwarp(qmask);
       if (leg == 0) as_int(S[S_EPISODE]) = episode;     // the record may be mid write-back by its own warp: this word decides
       __syncwarp(qmask);
-      reset_robot(S, E, Mo, E.cfg.gid0 + robot, leg, qmask);
+      reset_robot<OPT>(S, E, Mo, E.cfg.gid0 + robot, leg, qmask);
       __syncwarp(qmask);
       float4* dst = reinterpret_cast<float4*>(E.next_ep + (size_t)robot * ORL_STRIDE);
 #pragma unroll 1
@@ -594,7 +673,7 @@ ORL_DI void substep(const DevLeg& L, const DevModel& Mo, const PhysParams& P, co
 #ifndef ORL_STEP_MIN_BLOCKS
 #define ORL_STEP_MIN_BLOCKS (8 / ORL_WARPS_PER_BLOCK)
 #endif
-template <bool LAT>
+template <bool LAT, bool OPT>
 ORL_DI void step_worker(const DevEnv& E, unsigned char* smem, const float* __restrict__ actions, float* __restrict__ obs_out,
                         float* __restrict__ reward_out, uint8_t* __restrict__ done_out) {
 #ifdef ORL_PROFILE_RARE
@@ -851,6 +930,7 @@ ORL_DI void step_worker(const DevEnv& E, unsigned char* smem, const float* __res
   const float chk = pos.x + pos.y + pos.z + quat.x + quat.y + quat.z + quat.w + q[0] + q[1] + q[2] + qd[0] + qd[1] + qd[2] +
                     lin.x + lin.y + lin.z + ang.x + ang.y + ang.z;
   const int broken = quad_or(!(fabsf(chk) < 3.0e38f) ? 1 : 0);
+  if (OPT) reward *= C.reward_weight;                                  // imitation_task.py:356
   if (broken) reward = 0.f;
   __syncwarp();
 #ifdef ORL_PROFILE_RARE
@@ -858,12 +938,44 @@ ORL_DI void step_worker(const DevEnv& E, unsigned char* smem, const float* __res
 #endif
   // 5. task.update (imitation_task.py:201-207, 734-761, 1020-1055)
   RefFrame F = load_ref_frame(S, C);
-  const double time = motion_time(S, C);
-  const double new_phase = motion_phase(E.mt, F.clip, time);
+  double time = motion_time(S, C);
+  bool change = false;
+  double new_phase;
+  if (OPT) {
+    // clip switching (_update_ref_motion, imitation_task.py:740-746): a new clip, a new timer measured from the clock
+    // value BEFORE the new time offset is drawn, the new offset; the phase compared below is the NEW clip's at the OLD clock
+    change = time >= ld_f64(S + S_CHANGET) && E.mt.n_clips > 1;      // _check_change_clip :1096-1101
+    const unsigned qm = 0xFu << (lane & ~3);
+    if (change) {
+      const int nchange = as_int(S[S_NCHANGE]);
+      const int gid = C.gid0 + robot_c, ekey = as_int(S[S_EPISODE]) - 1;
+      uint32_t wa[4], wb[4];
+      opt_block(C, gid, ekey, ORL_CHANGE_BLOCK0 + 2u * (uint32_t)nchange, wa);
+      opt_block(C, gid, ekey, ORL_CHANGE_BLOCK0 + 1u + 2u * (uint32_t)nchange, wb);
+      const int nclip = (int)(((unsigned long long)wa[0] * (unsigned long long)E.mt.n_clips) >> 32);
+      const double dur_v = __dadd_rn(C.clip_tmin, __dmul_rn(__dsub_rn(C.clip_tmax, C.clip_tmin), u01_53(wa[2], wa[3])));
+      const double toff = __dadd_rn(0.0, __dmul_rn(__dsub_rn(E.mt.dur[nclip], 0.0), u01_53(wb[0], wb[1])));   // _sample_time_offset
+      __syncwarp(qm);                                   // every lane of the quad has read the old fields
+      if (leg == 0) {
+        as_int(S[S_CLIP]) = nclip; as_int(S[S_NCHANGE]) = nchange + 1;
+        st_f64(S + S_CHANGET, __dadd_rn(time, dur_v)); st_f64(S + S_TOFF, toff);
+      }
+      __syncwarp(qm);
+      F.clip = nclip;
+    }
+    new_phase = motion_phase(E.mt, F.clip, time);
+    if (change) time = motion_time(S, C);               // _sync_ref_origin / _update_ref_state re-read the clock (:1033, 765)
+  } else {
+    new_phase = motion_phase(E.mt, F.clip, time);
+  }
   const RefSample smp = ref_sample(E.mt, F, time);
   float3 nrp, nrl, nra; Q4 nrq;
   ref_root_raw(E.mt, F, smp, nrp, nrq);           // sampled once: the cycle-sync re-anchoring only moves the origin
-  if (C.cycle_sync && new_phase < ld_f64(S + S_PPHASE)) {
+  if (OPT && change) {                            // sync_root_rotation=change_clip (:1037-1045), heading rel. to the default rotation
+    const Q4 inv_def = qconj(ldq4(Mo->iquat));
+    F.origin_rot = qaxis_z(qheading(qmul(quat, inv_def)) - qheading(qmul(nrq, inv_def)));
+  }
+  if ((C.cycle_sync && new_phase < ld_f64(S + S_PPHASE)) || (OPT && change)) {
     float3 op = pos - qrot(F.origin_rot, nrp); op.z = 0.f;
     F.origin_pos = op;
   }
@@ -872,6 +984,7 @@ ORL_DI void step_worker(const DevEnv& E, unsigned char* smem, const float* __res
   __syncwarp();
   if (leg == 0) {
     st3(S + S_OPOS, F.origin_pos);
+    if (OPT && change) stq(S + S_OROT, F.origin_rot);
     st3(S + S_REFPOSE, nrp); stq(S + S_REFPOSE + 3, nrq); st3(S + S_REFVEL, nrl); st3(S + S_REFVEL + 3, nra);
     st_f64(S + S_PPHASE, new_phase);
   }
@@ -947,7 +1060,7 @@ ORL_DI void step_worker(const DevEnv& E, unsigned char* smem, const float* __res
       if (leg == 0 && valid) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
       __syncwarp(0xFu << (lane & ~3));
     }
-    finish_episode(S, E, *Mo, robot_c, leg, 0xFu << (lane & ~3), valid);
+    finish_episode<OPT>(S, E, *Mo, robot_c, leg, 0xFu << (lane & ~3), valid);
   }
 #ifdef ORL_PROFILE_RARE
   __syncwarp();
@@ -956,7 +1069,7 @@ ORL_DI void step_worker(const DevEnv& E, unsigned char* smem, const float* __res
 #endif
   __syncwarp();
   // 7. observation (histories + target frames)
-  build_obs(S, O, E, leg);
+  build_obs<OPT>(S, O, E, leg, C.gid0 + robot_c);
 #ifdef ORL_PROFILE_RARE
   __syncwarp();
   if (lane == 0) atomicAdd(&orl_prof[22], (unsigned long long)(clock64() - to0));
@@ -984,7 +1097,7 @@ ORL_DI void step_worker(const DevEnv& E, unsigned char* smem, const float* __res
 // The kernel: worker blocks first in the code (the position of the substep loop inside the kernel matters: every 20 KB
 // of code in front of it cost 6 us per step at N = 4096, profiles/r02_step_kernel.md "code placement"), the blocks that
 // prepare episodes after it.
-template <bool LAT>
+template <bool LAT, bool OPT>
 __global__ void __launch_bounds__(ORL_BLOCK_THREADS, ORL_STEP_MIN_BLOCKS) orl_step_kernel(DevEnv E, const float* __restrict__ actions, float* __restrict__ obs_out,
                                                       float* __restrict__ reward_out, uint8_t* __restrict__ done_out) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -996,11 +1109,12 @@ __global__ void __launch_bounds__(ORL_BLOCK_THREADS, ORL_STEP_MIN_BLOCKS) orl_st
     if (acc == 12345u) reward_out[0] = 1.f;
   }
 #endif
-  if ((int)blockIdx.x >= E.prep_blocks) { step_worker<LAT>(E, smem, actions, obs_out, reward_out, done_out); return; }
-  prepare_episodes(E, smem);
+  if ((int)blockIdx.x >= E.prep_blocks) { step_worker<LAT, OPT>(E, smem, actions, obs_out, reward_out, done_out); return; }
+  prepare_episodes<OPT>(E, smem);
 }
 
 // =================================================================================================
+template <bool OPT>
 __global__ void __launch_bounds__(ORL_BLOCK_THREADS) orl_reset_kernel(DevEnv E, const uint8_t* __restrict__ mask, float* __restrict__ obs_out) {
   extern __shared__ __align__(16) unsigned char smem[];
   const DevModel* Mo; float* st; float* ob;
@@ -1011,12 +1125,12 @@ __global__ void __launch_bounds__(ORL_BLOCK_THREADS) orl_reset_kernel(DevEnv E, 
   float* S = st + rw * ORL_STRIDE;
   const bool doit = mask == nullptr || mask[robot_c] != 0;
   if (doit) {
-    reset_robot(S, E, *Mo, E.cfg.gid0 + robot_c, leg, 0xFu << (lane & ~3));
+    reset_robot<OPT>(S, E, *Mo, E.cfg.gid0 + robot_c, leg, 0xFu << (lane & ~3));
     reset_rings(S, E, *Mo, E.cfg.gid0 + robot_c, leg, 0xFu << (lane & ~3), robot < E.cfg.n);
     if (robot < E.cfg.n && leg == 0) queue_for_preparation(E, robot);
   }
   __syncwarp();
-  build_obs(S, ob + rw * ORL_OBS_SIZE, E, leg);
+  build_obs<OPT>(S, ob + rw * ORL_OBS_SIZE, E, leg, E.cfg.gid0 + robot_c);
   stage_out(E, st, ob, obs_out);
 }
 

@@ -35,13 +35,14 @@
 #define S_ENVSTEP 260    // i32 env_step_counter (per robot; all equal without auto-reset)
 #define S_EPISODE 261    // i32 episode index (RNG counter)
 #define S_EPRET 262      // f32 return of the running episode
-// 263 pad
+#define S_NCHANGE 263    // i32 clip changes of the running episode (option kernels; RNG counter)
 #define S_OBSQ 264       // 4 base orientation (relative to the init orientation) of the control observation,
                          //   i.e. the state two substeps before the end of the control step (minitaur.py:336-357)
 #define S_STRENGTH 268   // 12 motor strength ratios (minitaur_motor.py:68-75)
 // domain randomizer (controllable_env_randomizer_from_config.py; values the robot setters receive)
 #define S_RAND 280       // 12: [0] base mass ratio [1] leg mass ratio [2] base inertia ratio [3] leg inertia ratio
                          //     [4] control latency (s; sampled, not applied yet) [5] foot lateral friction x plane friction
-                         //     (< 0: use the model's) [6..9] knee Coulomb friction torque per leg [10..11] pad
+                         //     (< 0: use the model's) [6..9] knee Coulomb friction torque per leg
+#define S_CHANGET 290    // f64 motion time of the next clip change (imitation_task.py:1057-1067; +inf: none)
 #define ORL_STRIDE 292   // multiple of 4 (float4) and of 2 (f64 fields stay 8-byte aligned)
 #define ORL_ROBOTS_PER_WARP 8

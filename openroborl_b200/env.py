@@ -19,7 +19,10 @@ TASK_DEFAULTS = dict(
     pose_weight=0.5, velocity_weight=0.05, end_effector_weight=0.2, root_pose_weight=0.15, root_velocity_weight=0.1,
     pose_err_scale=5.0, velocity_err_scale=0.1, end_effector_err_scale=40.0, end_effector_height_err_scale=3.0,
     root_pose_err_scale=20.0, root_velocity_err_scale=2.0, tar_frame_steps=(1, 2, 10, 30), ref_state_init_prob=0.9,
-    warmup_time=0.25, enable_cycle_sync=True, dist_fail_threshold=1.0, rot_fail_threshold=0.5 * math.pi)
+    warmup_time=0.25, enable_cycle_sync=True, dist_fail_threshold=1.0, rot_fail_threshold=0.5 * math.pi,
+    # options run.py leaves at their defaults (imitation_task.py:36-57); any other value selects the option kernels
+    weight=1.0, enable_rand_init_time=True, clip_time_min=math.inf, clip_time_max=math.inf, perturb_init_state_prob=0.0,
+    tar_obs_noise=None)
 # physics model of this repo (DESIGN.md "physics model"); gravity from quadruped_gym_env.py:200
 PHYS_DEFAULTS = dict(gravity_z=-10.0, contact_kn=1.0e5, contact_bn=500.0, contact_d0=0.002, contact_bt=3000.0,
                      limit_k=1000.0, limit_d=2.0, limit_e0=0.01, mu_plane=1.0, margin_factor=0.02,
@@ -29,14 +32,14 @@ RANDOMIZER_DEFAULTS = {"battery": (14.0, 16.8), "inertia": (0.5, 1.5), "joint fr
                        "lateral friction": (0.5, 1.25), "mass": (0.8, 1.2), "motor friction": (0.0, 0.05),
                        "motor strength": (0.8, 1.2)}
 
-_INT_FIELDS = ("clip", "warmup", "substep_counter", "step_counter", "env_step_counter", "episode")
-_F64_FIELDS = ("time_offset", "prev_phase")
+_INT_FIELDS = ("clip", "warmup", "substep_counter", "step_counter", "env_step_counter", "episode", "clip_changes")
+_F64_FIELDS = ("time_offset", "prev_phase", "clip_change_time")
 _FIELD_SHAPES = dict(
     pos=(3,), quat=(4,), q=(12,), lin=(3,), ang=(3,), qd=(12,), filt_x=(2, 12), filt_y=(2, 12), prev_filtered=(12,),
     ring1=(12,), ring2=(12,), imu_hist=(3, 4), act_hist=(3, 12), ang_hist=(3, 12), ref_pose=(19,), ref_vel=(18,),
     origin_pos=(3,), origin_rot=(4,), time_offset=(), prev_phase=(), clip=(), warmup=(), substep_counter=(),
     step_counter=(), env_step_counter=(), episode=(), ep_return=(), obs_quat=(4,), motor_strength=(12,),
-    rand_params=(12,))
+    rand_params=(10,), clip_change_time=(), clip_changes=())
 
 
 class OrlError(RuntimeError):
@@ -90,6 +93,13 @@ class BatchedImitationEnv(object):
         for k in ("gravity_z", "contact_kn", "contact_bn", "contact_d0", "contact_bt", "limit_k", "limit_d", "limit_e0",
                   "max_coordinate_velocity", "joint_friction_k", "mu_plane"):
             setattr(cfg, k, float(self.phys[k]))
+        cfg.reward_weight = float(self.task["weight"])
+        cfg.enable_rand_init_time = int(bool(self.task["enable_rand_init_time"]))
+        cfg.clip_time_min, cfg.clip_time_max = float(self.task["clip_time_min"]), float(self.task["clip_time_max"])
+        cfg.perturb_init_state_prob = float(self.task["perturb_init_state_prob"])
+        noise = self.task["tar_obs_noise"]
+        cfg.enable_tar_obs_noise = int(noise is not None)
+        cfg.tar_obs_noise = float(noise[0]) if noise is not None else 0.0
         # domain randomizer (run.py:205-211 enables it in train mode only)
         self.enable_randomizer = bool(enable_randomizer)
         self.randomizer_ranges = dict(RANDOMIZER_DEFAULTS, **(randomizer_ranges or {}))
@@ -321,6 +331,10 @@ class BatchedImitationEnv(object):
     def set_dynamics_rand(self, rand=None):
         """Randomizer values [n][12] (`rand_params` layout) for the next mass_matrix / inverse_dynamics /
         forward_dynamics calls; None restores the model's own parameters."""
+        if rand is not None:
+            rand = np.asarray(rand, dtype=np.float32)
+            if rand.shape[1] < 12:              # the state field has 10 values; the entry point strides by 12
+                rand = np.concatenate([rand, np.zeros((rand.shape[0], 12 - rand.shape[1]), np.float32)], axis=1)
         self._parity_rand = None if rand is None else self._dev(rand, 12)
         ptr = None if rand is None else C.c_void_p(self._parity_rand.data_ptr())
         self._check(self._lib.orl_set_dynamics_rand(self._h, ptr))
@@ -362,3 +376,36 @@ class BatchedImitationEnv(object):
         low[0:3], high[0:3], low[3:7], high[3:7] = -2, 2, -1, 1
         n = _abi.NUM_TAR_FRAMES
         return np.concatenate([-hi, np.tile(low, n)]), np.concatenate([hi, np.tile(high, n)])
+
+
+# minitaur_motor.py:24-37: per-motor layout of a HYBRID command and the control-mode constants
+MOTOR_COMMAND_DIMENSION = 5
+POSITION_INDEX, POSITION_GAIN_INDEX, VELOCITY_INDEX, VELOCITY_GAIN_INDEX, TORQUE_INDEX = 0, 1, 2, 3, 4
+MOTOR_POSITION, MOTOR_TORQUE, MOTOR_HYBRID = _abi.MOTOR_POSITION, _abi.MOTOR_TORQUE, _abi.MOTOR_HYBRID
+
+
+def motor_convert_to_torque(mode, commands, motor_angle=None, motor_velocity=None, kp=None, kd=None, strength=None,
+                            torque_limits=None):
+    """Batched MotorModel.convert_to_torque (minitaur_motor.py:104-173) on the device (orl_motor_convert_to_torque).
+
+    commands: CUDA float32 [n, 12] (POSITION: desired angles, TORQUE: torques) or [n, 60] (HYBRID); the other arguments
+    CUDA float32 tensors ([n, 12], kp / kd / torque_limits [12]) or None.  Returns the motor torques [n, 12]; the env step
+    itself is POSITION only, like the reference's (minitaur.py:113)."""
+    lib = _abi.load_library()
+    n = int(commands.shape[0])
+    width = _abi.NUM_MOTORS * (MOTOR_COMMAND_DIMENSION if mode == MOTOR_HYBRID else 1)
+    if tuple(commands.shape) != (n, width):
+        raise AssertionError("motor commands must have shape (n, %d)" % width)          # :139, 148, 155
+    ts = [commands, motor_angle, motor_velocity, kp, kd, strength, torque_limits]
+    for t in ts:
+        if t is not None and (not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous()):
+            raise ValueError("contiguous float32 CUDA tensors expected")
+    out = torch.empty((n, _abi.NUM_MOTORS), dtype=torch.float32, device=commands.device)
+    ptr = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+    with torch.cuda.device(commands.device):
+        rc = lib.orl_motor_convert_to_torque(int(mode), *[ptr(t) for t in ts], n, C.c_void_p(out.data_ptr()),
+                                             C.c_void_p(torch.cuda.current_stream(commands.device).cuda_stream))
+    if rc != 0:
+        raise ValueError("orl_motor_convert_to_torque: unsupported motor control mode or missing argument")    # :133-135
+    return out
+

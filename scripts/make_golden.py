@@ -163,6 +163,17 @@ def motion_kat(ref):
     qq, qd, cmd = rng.normal(size=(8, 12)), rng.normal(size=(8, 12)), rng.normal(size=(8, 12))
     out["motor/q"], out["motor/qd"], out["motor/cmd"] = qq, qd, cmd
     out["motor/tau"] = np.array([mm.convert_to_torque(c, a, b, b, minitaur_motor.POSITION)[0] for a, b, c in zip(qq, qd, cmd)])
+    # the other control modes, strength ratios and torque limits of the same class (minitaur_motor.py:137-171)
+    lim = rng.uniform(0.3, 2.0, size=12)
+    sr = rng.uniform(0.8, 1.2, size=12)
+    mm2 = minitaur_motor.MotorModel(kp=[220.0] * 12, kd=[0.3, 2.0, 2.0] * 4, torque_limits=lim)
+    mm2.set_strength_ratios(sr)
+    hyb = rng.normal(size=(8, 60))
+    hyb[:, 1::5] = rng.uniform(50.0, 250.0, size=(8, 12)); hyb[:, 3::5] = rng.uniform(0.3, 3.0, size=(8, 12))
+    out["motor/limits"], out["motor/strength"], out["motor/hybrid_cmd"] = lim, sr, hyb
+    out["motor/tau_position_limited"] = np.array([mm2.convert_to_torque(c, a, b, b, minitaur_motor.POSITION)[0] for a, b, c in zip(qq, qd, cmd)])
+    out["motor/tau_torque"] = np.array([mm2.convert_to_torque(c, a, b, b, minitaur_motor.TORQUE)[0] for a, b, c in zip(qq, qd, cmd)])
+    out["motor/tau_hybrid"] = np.array([mm2.convert_to_torque(c, a, b, b, minitaur_motor.HYBRID)[0] for a, b, c in zip(qq, qd, hyb)])
     np.savez_compressed(os.path.join(GOLD, "ref_motion_kat.npz"), **out)
     print("ref_motion_kat.npz:", len(out), "arrays")
 

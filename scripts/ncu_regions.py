@@ -13,7 +13,7 @@ col = {n: i for i, n in enumerate(hdr)}
 data = rows[2:]
 base = int(data[0][col["Address"]], 16)
 stalls = [n for n in hdr if n.startswith("stall_") and "Not Issued" not in n]
-ins = sass_sched.parse(sys.argv[2], "orl_step_kernelILb0")
+ins = sass_sched.parse(sys.argv[2], "orl_step_kernelILb0ELb0E")
 by_addr = {x["addr"]: i for i, x in enumerate(ins)}
 lp = [l for l in sass_sched.loops(ins) if l[0] // 16 <= 4000]
 nfp = lambda l: sum(1 for x in ins[by_addr[l[1]]:by_addr[l[2]] + 1] if x["base"] in ("FFMA", "FMUL", "FADD"))

@@ -73,7 +73,7 @@ def simulate(seq):
 
 def main():
     lib = sys.argv[1]
-    kern = sys.argv[2] if len(sys.argv) > 2 and not sys.argv[2].startswith("--") else "orl_step_kernelILb0"
+    kern = sys.argv[2] if len(sys.argv) > 2 and not sys.argv[2].startswith("--") else "orl_step_kernelILb0ELb0E"
     ins = parse(lib, kern)
     by_addr = {x["addr"]: i for i, x in enumerate(ins)}
     lp = loops(ins)

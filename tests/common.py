@@ -105,6 +105,9 @@ def sync_oracle_from_product(oracle, st, rings=None):
     oracle.prev_phase = f(st["prev_phase"])
     oracle.ref_pose, oracle.ref_vel = f(st["ref_pose"]), f(st["ref_vel"])
     oracle.motor_strength = f(st["motor_strength"])
+    if "clip_change_time" in st:
+        oracle.clip_change_time = f(st["clip_change_time"])
+        oracle.clip_changes = st["clip_changes"].astype(np.int64)
     if "rand_params" in st:
         load_rand_params(oracle, f(st["rand_params"]))
     # observation ring: entry 0 = current true state, entries 1/2 carry the delayed motor angles

@@ -117,3 +117,19 @@ def test_clamp_mode_clip_ends():
     assert np.array_equal(lib.is_over(clip, t), KAT[name + "/is_over"])
     assert KAT[name + "/is_over"].any() and not KAT[name + "/is_over"].all()
     assert set(np.unique(KAT[name + "/cycle"])) == {0, 1}
+
+
+def test_motor_model_all_modes_against_reference_class():
+    """minitaur_motor.py:104-173 with strength ratios and torque limits: POSITION, TORQUE (unclipped), HYBRID."""
+    from oracle import motor
+    q, qd, cmd = KAT["motor/q"], KAT["motor/qd"], KAT["motor/cmd"]
+    kp, kd = np.full(12, 220.0), np.array([0.3, 2.0, 2.0] * 4)
+    lim, sr, hyb = KAT["motor/limits"], KAT["motor/strength"], KAT["motor/hybrid_cmd"]
+    np.testing.assert_allclose(motor.convert_to_torque("position", cmd, q, qd, kp, kd), KAT["motor/tau"], rtol=0, atol=1e-12)
+    np.testing.assert_array_equal(motor.convert_to_torque("position", cmd, q, qd, kp, kd, sr, lim), KAT["motor/tau_position_limited"])
+    np.testing.assert_array_equal(motor.convert_to_torque("torque", cmd, q, qd, kp, kd, sr, lim), KAT["motor/tau_torque"])
+    np.testing.assert_array_equal(motor.convert_to_torque("hybrid", hyb, q, qd, None, None, sr, lim), KAT["motor/tau_hybrid"])
+    assert (np.abs(KAT["motor/tau_position_limited"]) == lim[None]).any()          # the limits do clip in the fixture
+    assert (np.abs(KAT["motor/tau_torque"]) > lim[None]).any()                     # TORQUE mode is returned before the clip
+    with pytest.raises(ValueError):
+        motor.convert_to_torque("pwm", cmd, q, qd, kp, kd)
