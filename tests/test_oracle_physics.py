@@ -79,3 +79,64 @@ def test_reset_draws_do_not_depend_on_sharding():
     full = common.make_oracle("laikago", ["laikago_pace"], 6, seed=11)
     part = common.make_oracle("laikago", ["laikago_pace"], 3, seed=11, gid0=3)
     assert np.array_equal(full.reset()[3:], part.reset())
+
+
+def _contact_point_heights(orc, frames):
+    k = orc.tree.fk(frames[:, 0:3], frames[:, 3:7], frames[:, 7:])
+    hs = []
+    for c in range(len(orc.cp_body)):
+        b = orc.cp_body[c]
+        P = k["x"][:, b] + np.einsum("nij,j->ni", k["R"][:, b], orc.cp_local[c])
+        hs.append(P[:, 2] - orc.cp_r[c])
+    return np.array(hs)                                    # (points, frames)
+
+
+def test_reference_clips_put_the_feet_of_the_urdf_fixtures_on_the_ground():
+    """A reference-held cross-check of the kinematic model (the URDFs of pybullet_data are not on
+    disk, openroborl_b200/assets holds fixtures written from the published geometry): the reference's motion clips were
+    retargeted onto the REAL robots, so forward kinematics of their frames with the right link lengths, joint offsets /
+    directions and toe radii puts the lowest collision point of every frame on the ground plane, never a body that is
+    not a foot link.  Every shipped clip (R/envs/quadruped_robot/task/motions/*.txt), all frames."""
+    import os
+    z = np.load(os.path.join(common.ROOT, "openroborl_b200", "assets", "motions", "clips.npz"), allow_pickle=True)
+    names = sorted(set(k.split("/")[0] for k in z.files) - {"synthetic_pace_clamp"})
+    assert len(names) == 11
+    for clip in names:
+        robot = "mini_cheetah" if clip.startswith("mini") else "laikago"
+        orc = common.make_oracle(robot, [clip], 1)
+        hs = _contact_point_heights(orc, orc.lib.frames)
+        low = hs.min(axis=0)                               # lowest collision point of each frame
+        foot = orc.cp_foot
+        assert foot[hs.argmin(axis=0)].all(), clip         # it is always a point of a foot link
+        assert hs[~foot].min() > 0.05, (clip, hs[~foot].min())          # chassis, hips, thighs stay clear of the ground
+        assert abs(np.median(low)) < 0.012, (clip, np.median(low))      # stance feet sit on the plane to ~1 cm
+        if clip != "laikago_hopturn":                                   # (the hop has a flight phase: 0.2 m)
+            assert low.max() < 0.035, (clip, low.max())
+        assert low.min() > -0.09, (clip, low.min())                     # worst frame of the 11 clips: laikago_sidesteps
+    # the symmetric gaits used by the bench workloads: within [-1 mm, +20 mm] over the whole clip
+    for clip in ("laikago_pace", "laikago_trot"):
+        orc = common.make_oracle("laikago", [clip], 1)
+        low = _contact_point_heights(orc, orc.lib.frames).min(axis=0)
+        assert -0.002 < low.min() and low.max() < 0.021, (clip, low.min(), low.max())
+
+
+def test_reference_clips_keep_stance_feet_in_place():
+    """Second reference-held check of the kinematic model (leg assignment, joint signs, JOINT_DIRECTIONS / JOINT_OFFSETS):
+    while a foot of the retargeted clip stands on the ground it must not travel with the trunk.  With two legs swapped or
+    a joint axis flipped the stance feet would move at least as fast as the root."""
+    for clip, robot in (("laikago_pace", "laikago"), ("laikago_trot", "laikago"), ("minicheetah_trot", "mini_cheetah")):
+        orc = common.make_oracle(robot, [clip], 1)
+        fr = orc.lib.frames
+        k = orc.tree.fk(fr[:, 0:3], fr[:, 3:7], fr[:, 7:])
+        P, H = [], []
+        for c in np.nonzero(orc.cp_foot)[0]:
+            b = orc.cp_body[c]
+            p = k["x"][:, b] + np.einsum("nij,j->ni", k["R"][:, b], orc.cp_local[c])
+            P.append(p); H.append(p[:, 2] - orc.cp_r[c])
+        P, H = np.array(P), np.array(H)
+        step = np.linalg.norm(np.diff(P[:, :, :2], axis=1), axis=-1)             # horizontal travel per frame
+        stance = (H[:, :-1] < 0.012) & (H[:, 1:] < 0.012)
+        root = np.median(np.linalg.norm(np.diff(fr[:, :2], axis=0), axis=-1))
+        assert stance.sum() >= 20, clip
+        assert np.median(step[stance]) < 0.45 * root, (clip, np.median(step[stance]), root)
+        assert np.median(step[~stance]) > 0.7 * root, (clip, np.median(step[~stance]), root)
