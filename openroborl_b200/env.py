@@ -205,14 +205,30 @@ class BatchedImitationEnv(object):
         return a, (o, r, d)
 
     def step_host(self, actions, out=None):
-        actions = np.ascontiguousarray(actions, dtype=np.float32)
-        if actions.shape != (self.num_robot, _abi.NUM_MOTORS):
+        # The same validated buffers as in the previous call (the usual loop): their addresses are known.  Building four
+        # `.ctypes.data` objects and re-validating took 5 of the ~125 us of a 4096-robot call.
+        c = getattr(self, "_host_call", None)
+        if c is not None and c[0] is actions and c[1] is out:
+            rc = self._lib.orl_step_host(self._h, *c[2])
+            if rc != 0:
+                self._check(rc)
+            return out
+        acts = np.ascontiguousarray(actions, dtype=np.float32)
+        if acts.shape != (self.num_robot, _abi.NUM_MOTORS):
             raise ValueError("actions must have shape (%d, 12)" % self.num_robot)
+        given = out
         if out is None:
             out = (np.empty((self.num_robot, _abi.OBS_SIZE), dtype=np.float32), np.empty(self.num_robot, dtype=np.float32),
                    np.empty(self.num_robot, dtype=np.uint8))
         obs, rew, done = out
-        self._check(self._lib.orl_step_host(self._h, actions.ctypes.data, obs.ctypes.data, rew.ctypes.data, done.ctypes.data))
+        shapes = ((self.num_robot, _abi.OBS_SIZE), (self.num_robot,), (self.num_robot,))
+        for a, dt, sh in zip(out, (np.float32, np.float32, np.uint8), shapes):
+            if not isinstance(a, np.ndarray) or a.dtype != dt or a.shape != sh or not a.flags.c_contiguous or not a.flags.writeable:
+                raise ValueError("output buffers must be writable C-contiguous arrays: obs float32 (N, 160), reward float32 (N,), done uint8 (N,)")
+        ptrs = (acts.ctypes.data, obs.ctypes.data, rew.ctypes.data, done.ctypes.data)
+        self._check(self._lib.orl_step_host(self._h, *ptrs))
+        # remember the call only when the caller's own arrays were used as they are (no converted copy of the actions)
+        self._host_call = (actions, given, ptrs) if (acts is actions and given is not None and isinstance(given, tuple)) else None
         return obs, rew, done
 
     def set_max_episode_steps(self, steps):
