@@ -10,6 +10,7 @@
 #include "orl_motion.cuh"
 #include "orl_dynamics.cuh"
 #include "orl_state.h"
+#define S_OBSW 37           // scratch in the record's padding: body-frame angular velocity of the control observation
 
 struct DevCfg {
   int n;                      // robots on this device
@@ -63,6 +64,13 @@ struct DevEnv {
   // observation buffer is mapped HOST memory, where it takes 1.1 of the 2.6 MB per step off the PCIe tail of the launch.
   // 0: one bulk copy of whole rows per warp at the end (device buffers: six small copies per robot only cost TMA issue slots).
   int obs_split;
+  // Reference packets computed ahead of the workers (profiles/r02_step_kernel.md section 9): everything the once-per-step
+  // code reads from the motion clips -- the reference sample at the end of this step and the four target frames of the
+  // observation -- only depends on (clip, warm-up flag, substep counter, time offset) of the record the launch starts
+  // from, so the leading blocks compute it while the workers are in the substep loop and the workers copy 480 bytes per
+  // robot instead of running five FP64 index computations, five quaternion slerps and 72 joint blends of cold code.
+  float* ahead;                       // [8 ceil(n / 8)][ORL_PK_STRIDE] (null: off)
+  int* ahead_flag;                    // [ceil(n / 8)] substep counter after this step of the chunk's first robot + 1 once the chunk is written
 };
 // ORL_LAT_RING (orl.h) = 42: latency <= 0.04 s = 40 substeps, entries E-41 .. E are live
 
@@ -210,17 +218,82 @@ ORL_DI double perturb_normal(const DevCfg& C, int gid, int episode, int i) {
   return (i & 1) ? normal_f64(w[2], w[3]) : normal_f64(w[0], w[1]);
 }
 
+// ---- reference packets ------------------------------------------------------------------------------
+// One row per robot; root pose / velocity BEFORE the per-episode origin (the cycle-sync re-anchoring of the update moves
+// the origin with the simulated robot, so the origin is applied by the consumer), joints, the phase / motion-over
+// results of the FP64 clock, the four target frames (root before the origin, joints), and the key the row was computed
+// from.  The same two producers run in the leading blocks (into global memory), in the blocks that prepare episodes
+// (target frames of the first observation of the next episode) and, when a row is missing, inline in the worker (into
+// the shared-memory copy of the row): one arithmetic, whoever runs it.
+#define PK_ROOT 0        // 3 + 4
+#define PK_VEL 7         // 3 + 3
+#define PK_J 13          // 12
+#define PK_JV 25         // 12
+#define PK_OVER 37       // i32 motion_is_over
+#define PK_PHASE 38      // f64
+#define PK_TAR 40        // 4 x 19
+#define PK_KEY 116       // i32 substep counter the row is for, i32 2 clip + warm, f64 time offset
+#define ORL_PK_STRIDE 120
+#define ORL_PK_TAR_FLOATS (19 * ORL_NUM_TAR_FRAMES)
+#define ORL_NEXT_STRIDE (ORL_STRIDE + ORL_PK_TAR_FLOATS)   // a prepared episode: its record + the target frames of its first observation
+static_assert(ORL_PK_STRIDE % 4 == 0 && PK_TAR % 4 == 0 && PK_PHASE % 2 == 0 && ORL_NEXT_STRIDE % 4 == 0, "packet rows are copied as float4");
+// ImitationTask._get_motion_time for a given substep counter (imitation_task.py:831-848)
+ORL_DI double motion_time_at(int substep, double toff, bool warm, const DevCfg& C) {
+  double t = __dmul_rn((double)substep, C.sim_dt);
+  t = __dadd_rn(t, toff);
+  t = __dadd_rn(t, -0.0);
+  if (warm) t = __dsub_rn(t, C.warmup_time);
+  return t;
+}
+// reference sample of task.update at `time`: every lane of the quad evaluates the sample, lane 0 stores the root part
+ORL_DI void produce_update(const MotionTables& T, const RefFrame& F, double time, float* pk, int leg) {
+  const RefSample smp = ref_sample(T, F, time);
+  float3 p, l, a; Q4 r;
+  ref_root_raw(T, F, smp, p, r);
+  ref_root_vel_raw(T, F, smp, l, a);
+  const double ph = motion_phase(T, F.clip, time);
+  if (leg == 0) {
+    st3(pk + PK_ROOT, p); stq(pk + PK_ROOT + 3, r); st3(pk + PK_VEL, l); st3(pk + PK_VEL + 3, a);
+    *reinterpret_cast<int*>(pk + PK_OVER) = motion_is_over(T, F.clip, time) ? 1 : 0;
+    *reinterpret_cast<double*>(pk + PK_PHASE) = ph;
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    pk[PK_J + 3 * leg + k] = ref_joint(T, F, smp, 3 * leg + k);
+    pk[PK_JV + 3 * leg + k] = ref_joint_vel(T, F, smp, 3 * leg + k);
+  }
+}
+// target frames of the observation built at clock value t0 (imitation_task.py:254-301): lane j evaluates frame j
+ORL_DI void produce_targets(const MotionTables& T, const RefFrame& F, double t0, const DevCfg& C, float* tar, int leg) {
+  const double tt = __dadd_rn(t0, __dmul_rn((double)C.tar_steps[leg], C.env_dt));
+  const RefSample s = ref_sample(T, F, tt);
+  float3 p; Q4 r;
+  ref_root_raw(T, F, s, p, r);
+  float* o = tar + 19 * leg;
+  st3(o, p); stq(o + 3, r);
+#pragma unroll 4
+  for (int j = 0; j < 12; ++j) o[7 + j] = ref_joint(T, F, s, j);
+}
+// shared-memory home of the warp's eight packet rows: behind the observation staging, inside the dynamics scratch (dead
+// once the substep loop is over)
+ORL_DI float* pk_rows(float* ob) { return ob + ORL_ROBOTS_PER_WARP * ORL_OBS_SIZE; }
+ORL_DI void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+
 // Observation rows: sensor histories (already in the record) + the target frames.
 // ImitationTask.build_target_obs (imitation_task.py:254-301): lane j of the quad builds frame j.
+// `tar`: this robot's target-frame block of its packet row; have_tar: it already holds the frames of the record's clock.
 template <bool OPT>
-ORL_DI void build_obs(float* S, float* O, const DevEnv& E, int leg, int gid) {
+ORL_DI void build_obs(float* S, float* O, const DevEnv& E, int leg, int gid, float* tar, bool have_tar) {
   const DevCfg& C = E.cfg;
   static_assert(S_IMU % 4 == 0 && ORL_STRIDE % 4 == 0 && ORL_OBS_SIZE % 4 == 0, "history block must be float4 aligned");
 #pragma unroll 1
   for (int i = leg; i < 21; i += 4)           // 84 floats of sensor history: the quad copies 21 float4
     reinterpret_cast<float4*>(O)[i] = reinterpret_cast<const float4*>(S + S_IMU)[i];
   const RefFrame F = load_ref_frame(S, C);
-  const double t0 = motion_time(S, C);
+  if (!have_tar) produce_targets(E.mt, F, motion_time(S, C), C, tar, leg);
+  __syncwarp();
   const float3 ref_base = ld3(S + S_REFPOSE);
   // robot.get_base_orientation(): delayed orientation -> euler -> quaternion (minitaur.py:513-527, 630-638)
   // Away from the gimbal branch of Bullet's ZYX euler extraction the heading of that round trip IS the yaw of the
@@ -245,16 +318,15 @@ ORL_DI void build_obs(float* S, float* O, const DevEnv& E, int leg, int gid) {
   }
   half_angle(sh, ch, shh, chh);
   const Q4 inv_rot = q4(0.f, 0.f, shh, chh);
-  const double tt = __dadd_rn(t0, __dmul_rn((double)C.tar_steps[leg], C.env_dt));
-  const RefSample s = ref_sample(E.mt, F, tt);
-  float3 p; Q4 r;
-  ref_root(E.mt, F, s, true, p, r);
+  const float* t = tar + 19 * leg;
+  float3 p = ld3(t); Q4 r = ldq(t + 3);
+  ref_apply_origin(F, p, r);
   p = qrot_z(sh, ch, p - ref_base);
   r = qstd(qmul(inv_rot, r));
   float* o = O + 84 + 19 * leg;
   st3(o, p); stq(o + 3, r);
-#pragma unroll 4
-  for (int j = 0; j < 12; ++j) o[7 + j] = ref_joint(E.mt, F, s, j);
+#pragma unroll
+  for (int j = 0; j < 12; ++j) o[7 + j] = t[7 + j];
 }
 
 // Episode reset of one robot, executed by its quad on the staged record.
@@ -297,6 +369,7 @@ ORL_DI void reset_robot(float* S, const DevEnv& E, const DevModel& Mo, int gid, 
     S[S_EPRET] = 0.f;
     st_f64(S + S_TOFF, toff);
     stq(S + S_OBSQ, q4(0.f, 0.f, 0.f, 1.f));
+    st3(S + S_OBSW, v3(0.f, 0.f, 0.f));          // scratch; written so that a record never carries bytes of an older episode
   }
   // domain randomizer (Minitaur.reset -> randomize_env, minitaur.py:273-276): ORL_RAND_DRAWS uniforms of this
   // (robot, episode), consumed in the reference's sorted parameter order; u = (word + 0.5) / 2^32
@@ -450,8 +523,10 @@ ORL_DI void queue_for_preparation(const DevEnv& E, int robot) {
   if (slot < 2 * E.cfg.n) E.todo[(size_t)list * 2 * E.cfg.n + slot] = robot;
 }
 // The whole in-kernel reset of one robot: from the prepared record when it is there, else computed on the spot.
+// Returns true when `tar` (the target-frame block of the robot's packet row) now holds the frames of the new episode's
+// first observation (they travel with the prepared record).
 template <bool OPT>
-ORL_DI void finish_episode(float* S, const DevEnv& E, const DevModel& Mo, int robot_c, int leg, unsigned qmask, bool valid) {
+ORL_DI bool finish_episode(float* S, const DevEnv& E, const DevModel& Mo, int robot_c, int leg, unsigned qmask, bool valid, float* tar) {
   bool ready = false;
   if (E.next_ep) {
     int have = 0;
@@ -460,9 +535,12 @@ ORL_DI void finish_episode(float* S, const DevEnv& E, const DevModel& Mo, int ro
     ready = have == as_int(S[S_EPISODE]) + 1;
   }
   if (ready) {                                          // (the acquire load of the flag orders the data loads after it)
-    const float4* src = reinterpret_cast<const float4*>(E.next_ep + (size_t)robot_c * ORL_STRIDE);
+    const float4* src = reinterpret_cast<const float4*>(E.next_ep + (size_t)robot_c * ORL_NEXT_STRIDE);
     float4* dst = reinterpret_cast<float4*>(S);
     __syncwarp(qmask);
+#pragma unroll 1
+    for (int i = leg; i < ORL_PK_TAR_FLOATS / 4; i += 4) cp_async16(reinterpret_cast<float4*>(tar) + i, src + ORL_STRIDE / 4 + i);
+    asm volatile("cp.async.commit_group;" ::: "memory");
     // all loads in flight before the first store (a rolled load-store loop paid one memory latency per float4: 19 in a row)
     constexpr int kPerLane = (ORL_STRIDE / 4 + 3) / 4;
     float4 v[kPerLane];
@@ -470,6 +548,7 @@ ORL_DI void finish_episode(float* S, const DevEnv& E, const DevModel& Mo, int ro
     for (int k = 0; k < kPerLane; ++k) { const int i = leg + 4 * k; if (i < ORL_STRIDE / 4) v[k] = __ldcg(src + i); }
 #pragma unroll
     for (int k = 0; k < kPerLane; ++k) { const int i = leg + 4 * k; if (i < ORL_STRIDE / 4) dst[i] = v[k]; }
+    asm volatile("cp.async.wait_all;" ::: "memory");
     __syncwarp(qmask);
   } else {
     reset_robot<OPT>(S, E, Mo, E.cfg.gid0 + robot_c, leg, qmask);
@@ -479,6 +558,7 @@ ORL_DI void finish_episode(float* S, const DevEnv& E, const DevModel& Mo, int ro
 #ifdef ORL_DEBUG_PREP
   if (valid && leg == 0) atomicAdd(E.stats + (ready ? 4 : 5), 1.0);
 #endif
+  return ready;
 }
 // Thread blocks [0, prep_blocks) of a step launch: one quad per queued robot (or, in scan mode, per robot of the batch
 // whose record is missing) writes the record of that robot's next episode.  Scratch records and a copy of the model
@@ -496,6 +576,7 @@ ORL_DI void prepare_episodes(const DevEnv& E, unsigned char* smem) {
   float* S = reinterpret_cast<float*>(smem + ORL_SMEM_MODEL_BYTES) + (size_t)(warp * ORL_ROBOTS_PER_WARP + rw) * ORL_STRIDE;
   const unsigned qmask = 0xFu << (lane & ~3);
   const int n = E.cfg.n;
+  if (!E.next_ep) return;
   const int quads = E.prep_blocks * ORL_ROBOTS_PER_BLOCK;
   const int count = E.prep_scan ? n : min(*reinterpret_cast<volatile const int*>(E.todo_count + E.prep_parity), 2 * n);
   const int* list = E.todo + (size_t)E.prep_parity * 2 * n;
@@ -525,14 +606,48 @@ ORL_DI void prepare_episodes(const DevEnv& E, unsigned char* smem) {
       __syncwarp(qmask);
       reset_robot<OPT>(S, E, Mo, E.cfg.gid0 + robot, leg, qmask);
       __syncwarp(qmask);
-      float4* dst = reinterpret_cast<float4*>(E.next_ep + (size_t)robot * ORL_STRIDE);
+      float4* dst = reinterpret_cast<float4*>(E.next_ep + (size_t)robot * ORL_NEXT_STRIDE);
 #pragma unroll 1
       for (int i = leg; i < ORL_STRIDE / 4; i += 4) __stcg(dst + i, rec[i]);
+      // target frames of the new episode's first observation (clock of the fresh record)
+      produce_targets(E.mt, load_ref_frame(S, E.cfg), motion_time(S, E.cfg), E.cfg, E.next_ep + (size_t)robot * ORL_NEXT_STRIDE + ORL_STRIDE, leg);
       __threadfence();                                  // the other three lanes' stores before the release below
       __syncwarp(qmask);
       if (leg == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(E.prepared + robot), "r"(episode + 1) : "memory");
     }
     __syncwarp();
+  }
+}
+
+// Thread blocks [0, prep_blocks) of a step launch, after the episodes: one quad per robot writes the packet row the
+// robot's worker reads when its substep loop is over.  The row is a pure function of four fields of the record the
+// launch starts from (they are stored with it as its key); a worker only takes a row whose key matches its own record.
+ORL_DI void reference_ahead(const DevEnv& E) {
+  if (!E.ahead) return;
+  const DevCfg& C = E.cfg;
+  const int lane = threadIdx.x & 31, leg = lane & 3, rw = lane >> 2, warp = threadIdx.x >> 5;
+  const int chunks = (C.n + ORL_ROBOTS_PER_WARP - 1) / ORL_ROBOTS_PER_WARP;
+  for (int chunk = (int)blockIdx.x * ORL_WARPS_PER_BLOCK + warp; chunk < chunks; chunk += E.prep_blocks * ORL_WARPS_PER_BLOCK) {
+    const int robot = chunk * ORL_ROBOTS_PER_WARP + rw;
+    const float* R = E.state + (size_t)min(robot, C.n - 1) * ORL_STRIDE;
+    const int clip = __float_as_int(__ldcg(R + S_CLIP)), warm = __float_as_int(__ldcg(R + S_WARM));
+    const int substep1 = __float_as_int(__ldcg(R + S_SUBSTEP)) + C.action_repeat;
+    const double toff = __ldcg(reinterpret_cast<const double*>(R + S_TOFF));
+    RefFrame F;
+    F.clip = min(max(clip, 0), E.mt.n_clips - 1); F.warmup = warm != 0; F.warmup_time = C.warmup_time;
+    F.origin_rot = q4(0.f, 0.f, 0.f, 1.f); F.origin_pos = v3(0.f, 0.f, 0.f);
+    const double time = motion_time_at(substep1, toff, warm != 0, C);
+    float* pk = E.ahead + (size_t)robot * ORL_PK_STRIDE;           // (the buffer has whole chunks: rows past the batch are scratch)
+    produce_update(E.mt, F, time, pk, leg);
+    produce_targets(E.mt, F, time, C, pk + PK_TAR, leg);
+    if (leg == 0) {
+      *reinterpret_cast<int*>(pk + PK_KEY) = substep1; *reinterpret_cast<int*>(pk + PK_KEY + 1) = 2 * clip + (warm != 0 ? 1 : 0);
+      *reinterpret_cast<double*>(pk + PK_KEY + 2) = toff;
+    }
+    __threadfence();
+    const int first = __shfl_sync(0xffffffffu, substep1, 0);
+    __syncwarp();
+    if (lane == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(E.ahead_flag + chunk), "r"(first + 1) : "memory");
   }
 }
 
@@ -561,7 +676,6 @@ struct LaneCtl {
   int capture;
   bool first_step;
 };
-#define S_OBSW 37           // scratch in the record's padding: body-frame angular velocity of the control observation
 
 // One 1 ms physics substep of this lane's leg (+ the redundantly integrated base).
 ORL_DI void cp_async4(float* smem_dst, const float* gmem_src) {
@@ -846,7 +960,13 @@ ORL_DI void step_worker(const DevEnv& E, unsigned char* smem, const float* __res
   }
   const Q4 obs_q = ldq(S + S_OBSQ);
   const float3 obs_w = ld3(S + S_OBSW);
+  // ---- reference packets of this warp's robots: requested now, read in sections 5 and 7 --------------------
+  float* const pk = pk_rows(ob) + rw * ORL_PK_STRIDE;
+  int ahead_have = 0;               // the flag is requested here and looked at behind the write-back (one L2 round trip)
+  if (!OPT && E.ahead && lane == 0)
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(ahead_have) : "l"(E.ahead_flag + warp_row0(E) / ORL_ROBOTS_PER_WARP) : "memory");
   // ---- write the dynamic state back to the record ---------------------------------------------------
+
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     S[S_Q + 3 * leg + k] = q[k]; S[S_QD + 3 * leg + k] = qd[k];
@@ -877,6 +997,21 @@ ORL_DI void step_worker(const DevEnv& E, unsigned char* smem, const float* __res
       bulk_s2g(row, smem_addr(S + S_IMU), 4 * 4);
       bulk_s2g(row + 48, smem_addr(S + S_ANGH), 12 * 4);
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  }
+  bool ahead = false;
+  if (!OPT && E.ahead) {
+    ahead = __shfl_sync(0xffffffffu, ahead_have, 0) == __shfl_sync(0xffffffffu, substep1, 0) + 1;   // (the acquire load orders the copies below after it)
+    if (ahead) {
+      const int nrow = min(ORL_ROBOTS_PER_WARP, C.n - warp_row0(E));
+      const float4* src = reinterpret_cast<const float4*>(E.ahead + (size_t)warp_row0(E) * ORL_PK_STRIDE);
+      float4* dst = reinterpret_cast<float4*>(pk_rows(ob));
+#pragma unroll 1
+      for (int i = lane; i < ORL_ROBOTS_PER_WARP * ORL_PK_STRIDE / 4; i += 32) {
+        const int row = i / (ORL_PK_STRIDE / 4), col = i - row * (ORL_PK_STRIDE / 4);
+        cp_async16(dst + i, src + min(row, nrow - 1) * (ORL_PK_STRIDE / 4) + col);       // idle quads: the last robot's row, like their record
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
     }
   }
 #ifdef ORL_PROFILE_RARE
@@ -938,9 +1073,21 @@ ORL_DI void step_worker(const DevEnv& E, unsigned char* smem, const float* __res
 #endif
   // 5. task.update (imitation_task.py:201-207, 734-761, 1020-1055)
   RefFrame F = load_ref_frame(S, C);
-  double time = motion_time(S, C);
+  if (ahead) {
+    // the rows have landed; a row is only good for the record it was computed from
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncwarp();
+    const bool match = as_int(pk[PK_KEY]) == as_int(S[S_SUBSTEP]) && as_int(pk[PK_KEY + 1]) == 2 * F.clip + (F.warmup ? 1 : 0) &&
+                       as_int(pk[PK_KEY + 2]) == as_int(S[S_TOFF]) && as_int(pk[PK_KEY + 3]) == as_int(S[S_TOFF + 1]);
+    ahead = __all_sync(0xffffffffu, match);
+  }
+#ifdef ORL_DEBUG_PREP
+  if (lane == 0) atomicAdd(E.stats + (ahead ? 6 : 7), 1.0);
+#endif
+  double time = 0.0;
   bool change = false;
   double new_phase;
+  if (!ahead) time = motion_time(S, C);
   if (OPT) {
     // clip switching (_update_ref_motion, imitation_task.py:740-746): a new clip, a new timer measured from the clock
     // value BEFORE the new time offset is drawn, the new offset; the phase compared below is the NEW clip's at the OLD clock
@@ -965,12 +1112,13 @@ ORL_DI void step_worker(const DevEnv& E, unsigned char* smem, const float* __res
     }
     new_phase = motion_phase(E.mt, F.clip, time);
     if (change) time = motion_time(S, C);               // _sync_ref_origin / _update_ref_state re-read the clock (:1033, 765)
-  } else {
-    new_phase = motion_phase(E.mt, F.clip, time);
   }
-  const RefSample smp = ref_sample(E.mt, F, time);
-  float3 nrp, nrl, nra; Q4 nrq;
-  ref_root_raw(E.mt, F, smp, nrp, nrq);           // sampled once: the cycle-sync re-anchoring only moves the origin
+  if (!ahead) produce_update(E.mt, F, time, pk, leg);       // no row from the leading blocks: the same arithmetic, here
+  __syncwarp();
+  if (!OPT) new_phase = ld_f64(pk + PK_PHASE);
+  const bool motion_over = as_int(pk[PK_OVER]) != 0;
+  float3 nrp = ld3(pk + PK_ROOT), nrl = ld3(pk + PK_VEL), nra = ld3(pk + PK_VEL + 3);
+  Q4 nrq = ldq(pk + PK_ROOT + 3);                 // sampled once: the cycle-sync re-anchoring only moves the origin
   if (OPT && change) {                            // sync_root_rotation=change_clip (:1037-1045), heading rel. to the default rotation
     const Q4 inv_def = qconj(ldq4(Mo->iquat));
     F.origin_rot = qaxis_z(qheading(qmul(quat, inv_def)) - qheading(qmul(nrq, inv_def)));
@@ -980,7 +1128,7 @@ ORL_DI void step_worker(const DevEnv& E, unsigned char* smem, const float* __res
     F.origin_pos = op;
   }
   ref_apply_origin(F, nrp, nrq);
-  ref_root_vel(E.mt, F, smp, nrl, nra);
+  nrl = qrot(F.origin_rot, nrl); nra = qrot(F.origin_rot, nra);
   __syncwarp();
   if (leg == 0) {
     st3(S + S_OPOS, F.origin_pos);
@@ -990,8 +1138,8 @@ ORL_DI void step_worker(const DevEnv& E, unsigned char* smem, const float* __res
   }
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
-    S[S_REFPOSE + 7 + 3 * leg + k] = ref_joint(E.mt, F, smp, 3 * leg + k);
-    S[S_REFVEL + 6 + 3 * leg + k] = ref_joint_vel(E.mt, F, smp, 3 * leg + k);
+    S[S_REFPOSE + 7 + 3 * leg + k] = pk[PK_J + 3 * leg + k];
+    S[S_REFVEL + 6 + 3 * leg + k] = pk[PK_JV + 3 * leg + k];
   }
 #ifdef ORL_PROFILE_RARE
   { const long long tn = clock64(); if (lane == 0) atomicAdd(&orl_prof[10], (unsigned long long)(tn - tsec)); tsec = tn; }
@@ -1024,7 +1172,7 @@ ORL_DI void step_worker(const DevEnv& E, unsigned char* smem, const float* __res
   {
     const float3 dp = nrp - pos;
     const float a = qangle_normalized(qmul(nrq, qconj(quat)));
-    done = motion_is_over(E.mt, F.clip, time) || fall || (dot(dp, dp) > C.dist_thr2) || (fabsf(a) > C.rot_thr);
+    done = motion_over || fall || (dot(dp, dp) > C.dist_thr2) || (fabsf(a) > C.rot_thr);
     done |= (envstep1 >= C.max_episode_steps) || broken;
   }
   __syncwarp();
@@ -1055,12 +1203,13 @@ ORL_DI void step_worker(const DevEnv& E, unsigned char* smem, const float* __res
   const long long tr0 = clock64();
   const bool any_finish = __any_sync(0xffffffffu, finish);
 #endif
+  bool have_tar = ahead && !(OPT && change);       // (a clip change moves the clock the target frames are read at)
   if (finish) {
     if (E.obs_split) {           // the early pieces of this row have landed before the record changes and the whole row follows
       if (leg == 0 && valid) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
       __syncwarp(0xFu << (lane & ~3));
     }
-    finish_episode<OPT>(S, E, *Mo, robot_c, leg, 0xFu << (lane & ~3), valid);
+    have_tar = finish_episode<OPT>(S, E, *Mo, robot_c, leg, 0xFu << (lane & ~3), valid, pk + PK_TAR);
   }
 #ifdef ORL_PROFILE_RARE
   __syncwarp();
@@ -1069,7 +1218,7 @@ ORL_DI void step_worker(const DevEnv& E, unsigned char* smem, const float* __res
 #endif
   __syncwarp();
   // 7. observation (histories + target frames)
-  build_obs<OPT>(S, O, E, leg, C.gid0 + robot_c);
+  build_obs<OPT>(S, O, E, leg, C.gid0 + robot_c, pk + PK_TAR, have_tar);
 #ifdef ORL_PROFILE_RARE
   __syncwarp();
   if (lane == 0) atomicAdd(&orl_prof[22], (unsigned long long)(clock64() - to0));
@@ -1111,6 +1260,7 @@ __global__ void __launch_bounds__(ORL_BLOCK_THREADS, ORL_STEP_MIN_BLOCKS) orl_st
 #endif
   if ((int)blockIdx.x >= E.prep_blocks) { step_worker<LAT, OPT>(E, smem, actions, obs_out, reward_out, done_out); return; }
   prepare_episodes<OPT>(E, smem);
+  if (!OPT) reference_ahead(E);
 }
 
 // =================================================================================================
@@ -1130,7 +1280,7 @@ __global__ void __launch_bounds__(ORL_BLOCK_THREADS) orl_reset_kernel(DevEnv E, 
     if (robot < E.cfg.n && leg == 0) queue_for_preparation(E, robot);
   }
   __syncwarp();
-  build_obs<OPT>(S, ob + rw * ORL_OBS_SIZE, E, leg, E.cfg.gid0 + robot_c);
+  build_obs<OPT>(S, ob + rw * ORL_OBS_SIZE, E, leg, E.cfg.gid0 + robot_c, pk_rows(ob) + rw * ORL_PK_STRIDE + PK_TAR, false);
   stage_out(E, st, ob, obs_out);
 }
 

@@ -180,9 +180,13 @@ ORL_DI float ref_joint(const MotionTables& T, const RefFrame& F, const RefSample
   return motion_joint(T, F.clip, s.b, j);
 }
 // ImitationTask._calc_ref_vel (imitation_task.py:955-983, 1011-1018)
-ORL_DI void ref_root_vel(const MotionTables& T, const RefFrame& F, const RefSample& s, float3& lin, float3& ang) {
+// root velocity of the sample before the per-episode origin rotation is applied
+ORL_DI void ref_root_vel_raw(const MotionTables& T, const RefFrame& F, const RefSample& s, float3& lin, float3& ang) {
   if (s.warm) { lin = v3(0.f, 0.f, 0.f); ang = v3(0.f, 0.f, 0.f); }
   else motion_root_vel(T, F.clip, s.b, s.co, lin, ang);
+}
+ORL_DI void ref_root_vel(const MotionTables& T, const RefFrame& F, const RefSample& s, float3& lin, float3& ang) {
+  ref_root_vel_raw(T, F, s, lin, ang);
   lin = qrot(F.origin_rot, lin);
   ang = qrot(F.origin_rot, ang);
 }
