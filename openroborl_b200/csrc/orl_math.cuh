@@ -119,10 +119,9 @@ ORL_DI void half_angle(float s, float c, float& sh, float& ch) {
 ORL_DI float qangle_normalized(Q4 q) {
   float n = sqrtf(q.x * q.x + q.y * q.y + q.z * q.z);
   float ang = 2.f * atan2f(n, q.w);
-  if (fabsf(ang) > ORL_PI_F) {
-    ang = fmodf(ang, ORL_TWO_PI_F);
-    ang += (ang >= 0.f) ? -ORL_TWO_PI_F : ORL_TWO_PI_F;
-  }
+  // n >= 0, so ang is in [0, 2 pi]: normalize_rotation_angle's fmod (motion_util.py) is the identity there, only its
+  // "> pi" branch can fire (an inline fmodf was 50 instructions of once-per-step code at each of the two call sites)
+  if (ang > ORL_PI_F) ang -= ORL_TWO_PI_F;
   return ang;
 }
 // pose3d.MapToMinusPiToPi
