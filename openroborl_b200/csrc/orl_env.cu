@@ -331,7 +331,7 @@ extern "C" int orl_create(const orl_config* cfg, const orl_robot_model* model, o
   }
   e->dev.ahead = nullptr; e->dev.ahead_flag = nullptr;
   {
-    static const char* off = getenv("ORL_AHEAD");                  // experiment knob: ORL_AHEAD=0 computes every packet inline
+    const char* off = getenv("ORL_AHEAD");                         // knob: ORL_AHEAD=0 computes every packet inline (tests compare the two)
     CUDA_TRY(e, cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, e->device));
     if (!(off && atoi(off) == 0)) {
       const size_t chunks = ((size_t)N + ORL_ROBOTS_PER_WARP - 1) / ORL_ROBOTS_PER_WARP;
@@ -559,7 +559,7 @@ static int step_launch(orl_env* e, const float* actions_dev, float* obs_dev, flo
     // substep loop from the instruction cache of that SM and the launch waits for those workers (8192 robots: 0.1351 ->
     // 0.1375 ms).  Idle SMs (<= 4608 robots: 0.0844 -> 0.0831 ms) or a grid of several waves (16384 robots: 0.2416 ->
     // 0.2320 ms) are the two cases that gain (profiles/r02_step_kernel.md section 9).
-    static const char* force = getenv("ORL_AHEAD");
+    const char* force = getenv("ORL_AHEAD");
     const bool one_full_wave = e->num_sms - blocks < 4 && blocks <= ORL_STEP_MIN_BLOCKS * e->num_sms;
     if (one_full_wave && !(force && atoi(force) == 2)) { d.ahead = nullptr; d.ahead_flag = nullptr; }
   }

@@ -536,6 +536,38 @@ def test_ragged_batch_with_randomizer_is_deterministic(N):
         assert np.array_equal(x, y)
 
 
+@pytest.mark.parametrize("robot,clips,N,rand", [("laikago", ["laikago_pace", "laikago_spin", "laikago_trot"], 2048 + 5, False),
+                                                ("minicheetah", ["minicheetah_trot"], 77, True)])
+def test_reference_packets_equal_the_inline_reference_evaluation(robot, clips, N, rand, monkeypatch):
+    """The leading blocks of a step launch compute the reference sample of task.update and the target frames of the
+    observation ahead of the workers (DevEnv::ahead); ORL_AHEAD=0 makes every worker compute them itself.  Both must give
+    the same bits: observations, rewards, done flags every step and the final records -- across in-kernel resets (short
+    episodes), cycle wraps of the clips, a ragged last warp, and records edited behind the library's back (a row whose
+    key no longer matches its record must be dropped, not used)."""
+    K = 24
+    acts = [torch.as_tensor(np.random.default_rng(300 + i).normal(scale=0.2, size=(N, 12)).astype(np.float32), device="cuda") for i in range(K)]
+
+    def run(flag):
+        monkeypatch.setenv("ORL_AHEAD", flag)
+        env = common.make_product(robot, clips, N, seed=11, auto_reset=True, randomizer=rand, max_episode_steps=9)
+        out = [env.reset().clone()]
+        for i, a in enumerate(acts):
+            if i == 10:                      # move the motion clock of every third robot by hand: old packets are now wrong
+                st = env.state.cpu().numpy().copy()
+                toff = st[:, env.layout["time_offset"]:env.layout["time_offset"] + 2].copy().view(np.float64)
+                toff[::3] += 0.0625
+                st[:, env.layout["time_offset"]:env.layout["time_offset"] + 2] = toff.view(np.float32)
+                env.state.copy_(torch.as_tensor(st, device=env.device))
+            out.extend(x.clone() for x in env.step(a))
+        out.append(env.state.clone())
+        env.close()
+        return out
+
+    on, off = run("1"), run("0")
+    for i, (x, y) in enumerate(zip(on, off)):
+        assert torch.equal(x.view(torch.uint8), y.view(torch.uint8)), i
+
+
 def test_time_limit_and_termination_thresholds(laikago):
     env, orc = laikago
     env.reset(); orc.reset()
