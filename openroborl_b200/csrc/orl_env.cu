@@ -29,7 +29,7 @@ struct orl_env {
   float* d_state;
   float* d_next_ep; int* d_prepared; int* d_todo; int* d_todo_count;   // episodes prepared ahead of time (auto-reset only)
   int prep_parity; bool prep_scan;
-  float* d_ahead; int* d_ahead_flag;   // reference packets computed ahead of the workers (DevEnv::ahead)
+  float* d_ahead; int ahead_parity; size_t ahead_bytes;   // reference packets computed one launch ahead (DevEnv::ahead)
   int num_sms;
   bool opt;                        // a task option of ABI 3 is on: the OPT instantiations of the step / reset kernels run
   DevModel* d_model;
@@ -227,7 +227,7 @@ extern "C" int orl_create(const orl_config* cfg, const orl_robot_model* model, o
   orl_env* e = new (std::nothrow) orl_env();
   if (!e) return ORL_ERR_INVALID;
   e->cfg = *cfg; e->model = *model; e->motions_loaded = false; e->launches = 0;
-  e->d_state = nullptr; e->d_model = nullptr; e->d_stats = nullptr; e->d_next_ep = nullptr; e->d_prepared = nullptr; e->d_todo = nullptr; e->d_todo_count = nullptr; e->prep_parity = 0; e->prep_scan = true; e->d_ahead = nullptr; e->d_ahead_flag = nullptr; e->num_sms = 0;
+  e->d_state = nullptr; e->d_model = nullptr; e->d_stats = nullptr; e->d_next_ep = nullptr; e->d_prepared = nullptr; e->d_todo = nullptr; e->d_todo_count = nullptr; e->prep_parity = 0; e->prep_scan = true; e->d_ahead = nullptr; e->ahead_parity = 0; e->ahead_bytes = 0; e->num_sms = 0;
   e->p_act = e->p_obs = e->p_rew = nullptr; e->p_done = e->p_mask = nullptr;
   e->d_act = e->d_obs = e->d_rew = nullptr; e->d_done = e->d_mask = nullptr;
   e->stream = nullptr;
@@ -329,17 +329,16 @@ extern "C" int orl_create(const orl_config* cfg, const orl_robot_model* model, o
     CUDA_TRY(e, cudaMemset(e->d_todo_count, 0, 2 * sizeof(int)));
     e->dev.next_ep = e->d_next_ep; e->dev.prepared = e->d_prepared; e->dev.todo = e->d_todo; e->dev.todo_count = e->d_todo_count;
   }
-  e->dev.ahead = nullptr; e->dev.ahead_flag = nullptr;
+  e->dev.ahead = nullptr; e->dev.ahead_parity = 0; e->dev.ahead_rows = 0;
   {
     const char* off = getenv("ORL_AHEAD");                         // knob: ORL_AHEAD=0 computes every packet inline (tests compare the two)
     CUDA_TRY(e, cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, e->device));
     if (!(off && atoi(off) == 0)) {
-      const size_t chunks = ((size_t)N + ORL_ROBOTS_PER_WARP - 1) / ORL_ROBOTS_PER_WARP;
-      CUDA_TRY(e, cudaMalloc(&e->d_ahead, chunks * ORL_ROBOTS_PER_WARP * ORL_PK_STRIDE * sizeof(float)));
-      CUDA_TRY(e, cudaMemset(e->d_ahead, 0, chunks * ORL_ROBOTS_PER_WARP * ORL_PK_STRIDE * sizeof(float)));
-      CUDA_TRY(e, cudaMalloc(&e->d_ahead_flag, chunks * sizeof(int)));
-      CUDA_TRY(e, cudaMemset(e->d_ahead_flag, 0, chunks * sizeof(int)));
-      e->dev.ahead = e->d_ahead; e->dev.ahead_flag = e->d_ahead_flag;
+      const size_t rows = (((size_t)N + ORL_ROBOTS_PER_WARP - 1) / ORL_ROBOTS_PER_WARP) * ORL_ROBOTS_PER_WARP;
+      e->ahead_bytes = 3 * rows * ORL_PK_STRIDE * sizeof(float);
+      CUDA_TRY(e, cudaMalloc(&e->d_ahead, e->ahead_bytes));
+      CUDA_TRY(e, cudaMemset(e->d_ahead, 0, e->ahead_bytes));        // key 0 matches no record that has been stepped
+      e->dev.ahead = e->d_ahead; e->dev.ahead_rows = (int)rows;
     }
   }
   if (cfg->enable_randomizer) {      // observation history for the randomised control latency
@@ -365,7 +364,7 @@ extern "C" int orl_destroy(orl_env* e) {
   free_motions(e);
   cudaFree(e->d_state); cudaFree(e->d_model); cudaFree(e->d_stats); cudaFree(e->dev.ring_q); cudaFree(e->dev.ring_b);
   cudaFree(e->d_next_ep); cudaFree(e->d_prepared); cudaFree(e->d_todo); cudaFree(e->d_todo_count);
-  cudaFree(e->d_ahead); cudaFree(e->d_ahead_flag);
+  cudaFree(e->d_ahead);
   cudaFreeHost(e->p_act); cudaFreeHost(e->p_obs); cudaFreeHost(e->p_rew); cudaFreeHost(e->p_done); cudaFreeHost(e->p_mask);
   cudaFree(e->d_act); cudaFree(e->d_obs); cudaFree(e->d_rew); cudaFree(e->d_done); cudaFree(e->d_mask);
   for (int i = 0; i < ORL_D2H_CHUNKS; ++i) if (e->ev_chunk[i]) cudaEventDestroy(e->ev_chunk[i]);
@@ -498,7 +497,7 @@ extern "C" int orl_load_motions(orl_env* e, const double* frames, const int32_t*
   if ((rc = upload(e, h_warm, &T.warm_pose))) return rc;
   T.n_clips = n_clips;
   if (e->d_prepared) { CUDA_TRY(e, cudaMemset(e->d_prepared, 0, (size_t)e->cfg.num_robot * sizeof(int))); e->prep_scan = true; }   // other clips, other episodes
-  if (e->d_ahead_flag) CUDA_TRY(e, cudaMemset(e->d_ahead_flag, 0, (((size_t)e->cfg.num_robot + ORL_ROBOTS_PER_WARP - 1) / ORL_ROBOTS_PER_WARP) * sizeof(int)));   // and other packets
+  if (e->d_ahead) CUDA_TRY(e, cudaMemset(e->d_ahead, 0, e->ahead_bytes));   // and other packets
   e->motions_loaded = true;
   return ORL_OK;
 }
@@ -553,7 +552,7 @@ static int step_launch(orl_env* e, const float* actions_dev, float* obs_dev, flo
   DevEnv d = e->dev;
   // leading blocks that prepare next episodes (they get the lowest block indices: scheduled first when the grid needs several waves)
   d.prep_blocks = d.next_ep ? std::min(16, std::max(1, (e->cfg.num_robot + 255) / 256)) : 0;
-  if (e->opt) { d.ahead = nullptr; d.ahead_flag = nullptr; }      // (clip switching moves the clock inside the step)
+  if (e->opt) d.ahead = nullptr;                                  // (clip switching moves the clock inside the step)
   {
     // Leading blocks that share an SM with worker blocks of the ONLY wave cost more than they save: their code evicts the
     // substep loop from the instruction cache of that SM and the launch waits for those workers (8192 robots: 0.1351 ->
@@ -561,7 +560,7 @@ static int step_launch(orl_env* e, const float* actions_dev, float* obs_dev, flo
     // 0.2320 ms) are the two cases that gain (profiles/r02_step_kernel.md section 9).
     const char* force = getenv("ORL_AHEAD");
     const bool one_full_wave = e->num_sms - blocks < 4 && blocks <= ORL_STEP_MIN_BLOCKS * e->num_sms;
-    if (one_full_wave && !(force && atoi(force) == 2)) { d.ahead = nullptr; d.ahead_flag = nullptr; }
+    if (one_full_wave && !(force && atoi(force) == 2)) d.ahead = nullptr;
   }
   if (d.ahead) {
     // reference packets: one quad-pass per robot; when the workers leave SMs idle (4096 robots = 128 of 148), all of them help
@@ -570,7 +569,8 @@ static int step_launch(orl_env* e, const float* actions_dev, float* obs_dev, flo
     d.prep_blocks = idle >= 4 ? std::min(idle, 32) : std::max(d.prep_blocks, std::min(64, std::max(1, chunks / 40)));
   }
   { static const char* ov = getenv("ORL_PREP_BLOCKS"); if (ov && (d.next_ep || d.ahead)) d.prep_blocks = atoi(ov); }   // experiment knob
-  if (d.prep_blocks == 0) { d.next_ep = nullptr; d.prepared = nullptr; d.todo = nullptr; d.ahead = nullptr; d.ahead_flag = nullptr; }
+  if (d.prep_blocks == 0) { d.next_ep = nullptr; d.prepared = nullptr; d.todo = nullptr; d.ahead = nullptr; }
+  d.ahead_parity = e->ahead_parity; e->ahead_parity ^= 1;         // this launch reads the half the previous one wrote
   d.prep_parity = e->prep_parity; d.prep_scan = e->prep_scan ? 1 : 0;
   d.obs_split = obs_split ? 1 : 0;
   e->prep_parity ^= 1; e->prep_scan = false;
@@ -740,7 +740,7 @@ extern "C" int orl_set_state_host(orl_env* e, const float* state) {
   CUDA_TRY(e, cudaDeviceSynchronize());
   CUDA_TRY(e, cudaMemcpy(e->d_state, state, (size_t)e->cfg.num_robot * ORL_STRIDE * sizeof(float), cudaMemcpyHostToDevice));
   e->prep_scan = true;                 // episode counters may have moved: the next launch checks every robot's prepared record
-  if (e->d_ahead_flag) CUDA_TRY(e, cudaMemset(e->d_ahead_flag, 0, (((size_t)e->cfg.num_robot + ORL_ROBOTS_PER_WARP - 1) / ORL_ROBOTS_PER_WARP) * sizeof(int)));
+  if (e->d_ahead) CUDA_TRY(e, cudaMemset(e->d_ahead, 0, e->ahead_bytes));
   return ORL_OK;
 }
 

@@ -64,13 +64,19 @@ struct DevEnv {
   // observation buffer is mapped HOST memory, where it takes 1.1 of the 2.6 MB per step off the PCIe tail of the launch.
   // 0: one bulk copy of whole rows per warp at the end (device buffers: six small copies per robot only cost TMA issue slots).
   int obs_split;
-  // Reference packets computed ahead of the workers (profiles/r02_step_kernel.md section 9): everything the once-per-step
-  // code reads from the motion clips -- the reference sample at the end of this step and the four target frames of the
-  // observation -- only depends on (clip, warm-up flag, substep counter, time offset) of the record the launch starts
-  // from, so the leading blocks compute it while the workers are in the substep loop and the workers copy 480 bytes per
+  // Reference packets computed one launch ahead (profiles/r02_step_kernel.md section 9): everything the once-per-step code
+  // reads from the motion clips -- the reference sample at the end of a step and the four target frames of its observation
+  // -- only depends on (clip, warm-up flag, substep counter, time offset).  Unless a robot is reset, the record of the NEXT
+  // launch has the same clip / flag / offset and a counter that is one control step further, so the leading blocks of this
+  // launch compute the NEXT launch's row of every robot while the workers are in the substep loop (a robot that is reset
+  // gets the row of its new episode's first step from the prepared episode instead).  The workers copy 480 bytes per
   // robot instead of running five FP64 index computations, five quaternion slerps and 72 joint blends of cold code.
-  float* ahead;                       // [8 ceil(n / 8)][ORL_PK_STRIDE] (null: off)
-  int* ahead_flag;                    // [ceil(n / 8)] substep counter after this step of the chunk's first robot + 1 once the chunk is written
+  // [3][8 ceil(n / 8)][ORL_PK_STRIDE]: part `ahead_parity` (0 / 1) is read by this launch, the other one written by its
+  // leading blocks; part 2 holds the first-step rows of freshly started episodes, written by the reset (sole writer per
+  // robot, so a late leading block can never mix its bytes into such a row) and read while the substep counter is 0
+  float* ahead;                       // (null: off)
+  int ahead_parity;
+  int ahead_rows;                     // rows per half
 };
 // ORL_LAT_RING (orl.h) = 42: latency <= 0.04 s = 40 substeps, entries E-41 .. E are live
 
@@ -235,7 +241,7 @@ ORL_DI double perturb_normal(const DevCfg& C, int gid, int episode, int i) {
 #define PK_KEY 116       // i32 substep counter the row is for, i32 2 clip + warm, f64 time offset
 #define ORL_PK_STRIDE 120
 #define ORL_PK_TAR_FLOATS (19 * ORL_NUM_TAR_FRAMES)
-#define ORL_NEXT_STRIDE (ORL_STRIDE + ORL_PK_TAR_FLOATS)   // a prepared episode: its record + the target frames of its first observation
+#define ORL_NEXT_STRIDE (ORL_STRIDE + ORL_PK_TAR_FLOATS + ORL_PK_STRIDE)   // a prepared episode: its record, the target frames of its first observation, the packet row of its first step
 static_assert(ORL_PK_STRIDE % 4 == 0 && PK_TAR % 4 == 0 && PK_PHASE % 2 == 0 && ORL_NEXT_STRIDE % 4 == 0, "packet rows are copied as float4");
 // ImitationTask._get_motion_time for a given substep counter (imitation_task.py:831-848)
 ORL_DI double motion_time_at(int substep, double toff, bool warm, const DevCfg& C) {
@@ -273,6 +279,20 @@ ORL_DI void produce_targets(const MotionTables& T, const RefFrame& F, double t0,
   st3(o, p); stq(o + 3, r);
 #pragma unroll 4
   for (int j = 0; j < 12; ++j) o[7 + j] = ref_joint(T, F, s, j);
+}
+// One complete row for the step that ENDS with substep counter `substep1` (what reference_ahead, prepare_episodes and --
+// through the two producers -- the inline fallback of the worker compute).
+ORL_DI void produce_row(const MotionTables& T, const DevCfg& C, int clip, bool warm, double toff, int substep1, float* pk, int leg) {
+  RefFrame F;
+  F.clip = clip; F.warmup = warm; F.warmup_time = C.warmup_time;
+  F.origin_rot = q4(0.f, 0.f, 0.f, 1.f); F.origin_pos = v3(0.f, 0.f, 0.f);
+  const double time = motion_time_at(substep1, toff, warm, C);
+  produce_update(T, F, time, pk, leg);
+  produce_targets(T, F, time, C, pk + PK_TAR, leg);
+  if (leg == 0) {
+    *reinterpret_cast<int*>(pk + PK_KEY) = substep1; *reinterpret_cast<int*>(pk + PK_KEY + 1) = 2 * clip + (warm ? 1 : 0);
+    *reinterpret_cast<double*>(pk + PK_KEY + 2) = toff;
+  }
 }
 // shared-memory home of the warp's eight packet rows: behind the observation staging, inside the dynamics scratch (dead
 // once the substep loop is over)
@@ -546,8 +566,18 @@ ORL_DI bool finish_episode(float* S, const DevEnv& E, const DevModel& Mo, int ro
     float4 v[kPerLane];
 #pragma unroll
     for (int k = 0; k < kPerLane; ++k) { const int i = leg + 4 * k; if (i < ORL_STRIDE / 4) v[k] = __ldcg(src + i); }
+    // the new episode's first step finds its packet row like every other step: same round trip as the record
+    const bool row = E.ahead && valid;
+    const float4* rsrc = src + (ORL_STRIDE + ORL_PK_TAR_FLOATS) / 4;
+    float4* rdst = reinterpret_cast<float4*>(E.ahead + ((size_t)2 * E.ahead_rows + robot_c) * ORL_PK_STRIDE);
+    constexpr int kRow = (ORL_PK_STRIDE / 4 + 3) / 4;
+    float4 w[kRow];
+#pragma unroll
+    for (int k = 0; k < kRow; ++k) { const int i = leg + 4 * k; if (row && i < ORL_PK_STRIDE / 4) w[k] = __ldcg(rsrc + i); }
 #pragma unroll
     for (int k = 0; k < kPerLane; ++k) { const int i = leg + 4 * k; if (i < ORL_STRIDE / 4) dst[i] = v[k]; }
+#pragma unroll
+    for (int k = 0; k < kRow; ++k) { const int i = leg + 4 * k; if (row && i < ORL_PK_STRIDE / 4) __stcg(rdst + i, w[k]); }
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncwarp(qmask);
   } else {
@@ -611,6 +641,9 @@ ORL_DI void prepare_episodes(const DevEnv& E, unsigned char* smem) {
       for (int i = leg; i < ORL_STRIDE / 4; i += 4) __stcg(dst + i, rec[i]);
       // target frames of the new episode's first observation (clock of the fresh record)
       produce_targets(E.mt, load_ref_frame(S, E.cfg), motion_time(S, E.cfg), E.cfg, E.next_ep + (size_t)robot * ORL_NEXT_STRIDE + ORL_STRIDE, leg);
+      // and the packet row of its first step (substep counter 0 -> action_repeat)
+      if (!OPT) produce_row(E.mt, E.cfg, as_int(S[S_CLIP]), as_int(S[S_WARM]) != 0, ld_f64(S + S_TOFF), E.cfg.action_repeat,
+                            E.next_ep + (size_t)robot * ORL_NEXT_STRIDE + ORL_STRIDE + ORL_PK_TAR_FLOATS, leg);
       __threadfence();                                  // the other three lanes' stores before the release below
       __syncwarp(qmask);
       if (leg == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(E.prepared + robot), "r"(episode + 1) : "memory");
@@ -619,35 +652,24 @@ ORL_DI void prepare_episodes(const DevEnv& E, unsigned char* smem) {
   }
 }
 
-// Thread blocks [0, prep_blocks) of a step launch, after the episodes: one quad per robot writes the packet row the
-// robot's worker reads when its substep loop is over.  The row is a pure function of four fields of the record the
-// launch starts from (they are stored with it as its key); a worker only takes a row whose key matches its own record.
+// Thread blocks [0, prep_blocks) of a step launch, after the episodes: one quad per robot writes the packet row the robot's
+// worker will read in the NEXT launch (unless the robot is reset in this one: finish_episode then replaces the row).  A row
+// is a pure function of four fields of the record (stored with it as its key); a worker only takes a row whose key matches.
 ORL_DI void reference_ahead(const DevEnv& E) {
   if (!E.ahead) return;
   const DevCfg& C = E.cfg;
   const int lane = threadIdx.x & 31, leg = lane & 3, rw = lane >> 2, warp = threadIdx.x >> 5;
   const int chunks = (C.n + ORL_ROBOTS_PER_WARP - 1) / ORL_ROBOTS_PER_WARP;
+  float* half = E.ahead + (size_t)(E.ahead_parity ^ 1) * E.ahead_rows * ORL_PK_STRIDE;
   for (int chunk = (int)blockIdx.x * ORL_WARPS_PER_BLOCK + warp; chunk < chunks; chunk += E.prep_blocks * ORL_WARPS_PER_BLOCK) {
     const int robot = chunk * ORL_ROBOTS_PER_WARP + rw;
     const float* R = E.state + (size_t)min(robot, C.n - 1) * ORL_STRIDE;
     const int clip = __float_as_int(__ldcg(R + S_CLIP)), warm = __float_as_int(__ldcg(R + S_WARM));
-    const int substep1 = __float_as_int(__ldcg(R + S_SUBSTEP)) + C.action_repeat;
+    const int substep2 = __float_as_int(__ldcg(R + S_SUBSTEP)) + 2 * C.action_repeat;
     const double toff = __ldcg(reinterpret_cast<const double*>(R + S_TOFF));
-    RefFrame F;
-    F.clip = min(max(clip, 0), E.mt.n_clips - 1); F.warmup = warm != 0; F.warmup_time = C.warmup_time;
-    F.origin_rot = q4(0.f, 0.f, 0.f, 1.f); F.origin_pos = v3(0.f, 0.f, 0.f);
-    const double time = motion_time_at(substep1, toff, warm != 0, C);
-    float* pk = E.ahead + (size_t)robot * ORL_PK_STRIDE;           // (the buffer has whole chunks: rows past the batch are scratch)
-    produce_update(E.mt, F, time, pk, leg);
-    produce_targets(E.mt, F, time, C, pk + PK_TAR, leg);
-    if (leg == 0) {
-      *reinterpret_cast<int*>(pk + PK_KEY) = substep1; *reinterpret_cast<int*>(pk + PK_KEY + 1) = 2 * clip + (warm != 0 ? 1 : 0);
-      *reinterpret_cast<double*>(pk + PK_KEY + 2) = toff;
-    }
-    __threadfence();
-    const int first = __shfl_sync(0xffffffffu, substep1, 0);
+    // (the buffer has whole chunks: rows past the batch are scratch; a clip index read mid write-back is clamped, its row's key will not match)
+    produce_row(E.mt, C, min(max(clip, 0), E.mt.n_clips - 1), warm != 0, toff, substep2, half + (size_t)robot * ORL_PK_STRIDE, leg);
     __syncwarp();
-    if (lane == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(E.ahead_flag + chunk), "r"(first + 1) : "memory");
   }
 }
 
@@ -962,9 +984,19 @@ ORL_DI void step_worker(const DevEnv& E, unsigned char* smem, const float* __res
   const float3 obs_w = ld3(S + S_OBSW);
   // ---- reference packets of this warp's robots: requested now, read in sections 5 and 7 --------------------
   float* const pk = pk_rows(ob) + rw * ORL_PK_STRIDE;
-  int ahead_have = 0;               // the flag is requested here and looked at behind the write-back (one L2 round trip)
-  if (!OPT && E.ahead && lane == 0)
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(ahead_have) : "l"(E.ahead_flag + warp_row0(E) / ORL_ROBOTS_PER_WARP) : "memory");
+  bool ahead = !OPT && E.ahead != nullptr;
+  if (ahead) {        // written by the previous launch: no flag to wait for, the copies overlap the write-back and the reward
+    const int nrow = min(ORL_ROBOTS_PER_WARP, C.n - warp_row0(E));
+    const float4* src = reinterpret_cast<const float4*>(E.ahead) + (size_t)warp_row0(E) * (ORL_PK_STRIDE / 4);
+    float4* dst = reinterpret_cast<float4*>(pk_rows(ob));
+#pragma unroll 1
+    for (int i = lane; i < ORL_ROBOTS_PER_WARP * ORL_PK_STRIDE / 4; i += 32) {
+      const int row = i / (ORL_PK_STRIDE / 4), col = i - row * (ORL_PK_STRIDE / 4);
+      const int part = as_int(st[row * ORL_STRIDE + S_SUBSTEP]) == 0 ? 2 : E.ahead_parity;      // first step of an episode: the row its reset left
+      cp_async16(dst + i, src + ((size_t)part * E.ahead_rows + min(row, nrow - 1)) * (ORL_PK_STRIDE / 4) + col);   // idle quads: the last robot's row, like their record
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
   // ---- write the dynamic state back to the record ---------------------------------------------------
 
 #pragma unroll
@@ -997,21 +1029,6 @@ ORL_DI void step_worker(const DevEnv& E, unsigned char* smem, const float* __res
       bulk_s2g(row, smem_addr(S + S_IMU), 4 * 4);
       bulk_s2g(row + 48, smem_addr(S + S_ANGH), 12 * 4);
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    }
-  }
-  bool ahead = false;
-  if (!OPT && E.ahead) {
-    ahead = __shfl_sync(0xffffffffu, ahead_have, 0) == __shfl_sync(0xffffffffu, substep1, 0) + 1;   // (the acquire load orders the copies below after it)
-    if (ahead) {
-      const int nrow = min(ORL_ROBOTS_PER_WARP, C.n - warp_row0(E));
-      const float4* src = reinterpret_cast<const float4*>(E.ahead + (size_t)warp_row0(E) * ORL_PK_STRIDE);
-      float4* dst = reinterpret_cast<float4*>(pk_rows(ob));
-#pragma unroll 1
-      for (int i = lane; i < ORL_ROBOTS_PER_WARP * ORL_PK_STRIDE / 4; i += 32) {
-        const int row = i / (ORL_PK_STRIDE / 4), col = i - row * (ORL_PK_STRIDE / 4);
-        cp_async16(dst + i, src + min(row, nrow - 1) * (ORL_PK_STRIDE / 4) + col);       // idle quads: the last robot's row, like their record
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
     }
   }
 #ifdef ORL_PROFILE_RARE
@@ -1074,15 +1091,14 @@ ORL_DI void step_worker(const DevEnv& E, unsigned char* smem, const float* __res
   // 5. task.update (imitation_task.py:201-207, 734-761, 1020-1055)
   RefFrame F = load_ref_frame(S, C);
   if (ahead) {
-    // the rows have landed; a row is only good for the record it was computed from
+    // the rows have landed; a row is only good for the record it was computed from (quad-uniform)
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncwarp();
-    const bool match = as_int(pk[PK_KEY]) == as_int(S[S_SUBSTEP]) && as_int(pk[PK_KEY + 1]) == 2 * F.clip + (F.warmup ? 1 : 0) &&
-                       as_int(pk[PK_KEY + 2]) == as_int(S[S_TOFF]) && as_int(pk[PK_KEY + 3]) == as_int(S[S_TOFF + 1]);
-    ahead = __all_sync(0xffffffffu, match);
+    ahead = as_int(pk[PK_KEY]) == as_int(S[S_SUBSTEP]) && as_int(pk[PK_KEY + 1]) == 2 * F.clip + (F.warmup ? 1 : 0) &&
+            as_int(pk[PK_KEY + 2]) == as_int(S[S_TOFF]) && as_int(pk[PK_KEY + 3]) == as_int(S[S_TOFF + 1]);
   }
 #ifdef ORL_DEBUG_PREP
-  if (lane == 0) atomicAdd(E.stats + (ahead ? 6 : 7), 1.0);
+  if (leg == 0 && valid) atomicAdd(E.stats + (ahead ? 6 : 7), 1.0);
 #endif
   double time = 0.0;
   bool change = false;
@@ -1259,8 +1275,8 @@ __global__ void __launch_bounds__(ORL_BLOCK_THREADS, ORL_STEP_MIN_BLOCKS) orl_st
   }
 #endif
   if ((int)blockIdx.x >= E.prep_blocks) { step_worker<LAT, OPT>(E, smem, actions, obs_out, reward_out, done_out); return; }
+  if (!OPT) reference_ahead(E);        // first: ~50 k cycles at 4096 robots, and the episodes are only needed when a step ends
   prepare_episodes<OPT>(E, smem);
-  if (!OPT) reference_ahead(E);
 }
 
 // =================================================================================================

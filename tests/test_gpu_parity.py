@@ -568,6 +568,39 @@ def test_reference_packets_equal_the_inline_reference_evaluation(robot, clips, N
         assert torch.equal(x.view(torch.uint8), y.view(torch.uint8)), i
 
 
+@pytest.mark.parametrize("N,rand", [(1024 + 3, False), (200, True)])
+def test_host_buffer_steps_with_packet_rows_equal_the_device_api(N, rand, monkeypatch):
+    """orl_step_host with page-locked buffers ships the observation row in pieces (DevEnv::obs_split) while the reference part
+    of it comes out of packet rows computed one launch ahead.  Every step's row must equal the device API's, bit for bit,
+    across in-kernel resets (short episodes: a reset robot rewrites its whole row, its next row comes from the prepared
+    episode) and a ragged last warp, and equal the same API with ORL_AHEAD=0 (every packet computed inline)."""
+    K = 30
+    rng = np.random.default_rng(9)
+    acts = [rng.normal(scale=0.2, size=(N, 12)).astype(np.float32) for _ in range(K)]
+
+    def run(flag, host):
+        monkeypatch.setenv("ORL_AHEAD", flag)
+        env = common.make_product("laikago", ["laikago_pace", "laikago_trot"], N, seed=4, auto_reset=True, randomizer=rand, max_episode_steps=7)
+        out = []
+        if host:
+            pa, pout = env.alloc_host_buffers()
+            out.append(env.reset_host().copy())
+            for a in acts:
+                pa[...] = a
+                out.extend(np.array(x).copy() for x in env.step_host(pa, pout))
+        else:
+            out.append(env.reset().cpu().numpy())
+            for a in acts:
+                out.extend(x.cpu().numpy() for x in env.step(torch.as_tensor(a, device=env.device)))
+        env.close()
+        return out
+
+    dev, host_on, host_off = run("1", False), run("1", True), run("0", True)
+    for i, (x, y, z) in enumerate(zip(dev, host_on, host_off)):
+        assert np.array_equal(x.view(np.uint8), y.view(np.uint8)), i
+        assert np.array_equal(x.view(np.uint8), z.view(np.uint8)), i
+
+
 def test_time_limit_and_termination_thresholds(laikago):
     env, orc = laikago
     env.reset(); orc.reset()
