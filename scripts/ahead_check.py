@@ -20,6 +20,7 @@ def child(out):
     from tests import common
     res = {}
     for ci, (robot, clips, N, rand, K) in enumerate(CASES):
+        K = K * int(os.environ.get("AHEAD_SOAK", "1"))             # AHEAD_SOAK=25: 1500-step runs (rare interleavings)
         env = common.make_product(robot, clips.split(","), N, seed=5, auto_reset=True, randomizer=rand)
         obs = env.reset()
         gen = torch.Generator(device=env.device); gen.manual_seed(77)
