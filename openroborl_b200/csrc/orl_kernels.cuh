@@ -652,9 +652,10 @@ ORL_DI void prepare_episodes(const DevEnv& E, unsigned char* smem) {
   }
 }
 
-// Thread blocks [0, prep_blocks) of a step launch, after the episodes: one quad per robot writes the packet row the robot's
-// worker will read in the NEXT launch (unless the robot is reset in this one: finish_episode then replaces the row).  A row
-// is a pure function of four fields of the record (stored with it as its key); a worker only takes a row whose key matches.
+// Thread blocks [0, prep_blocks) of a step launch, before they prepare episodes: one quad per robot writes the packet row the
+// robot's worker will read in the NEXT launch (unless the robot is reset in this one: its worker then reads the row
+// finish_episode left in part 2).  A row is a pure function of four fields of the record (stored with it as its key); a
+// worker only takes a row whose key matches.
 ORL_DI void reference_ahead(const DevEnv& E) {
   if (!E.ahead) return;
   const DevCfg& C = E.cfg;
