@@ -553,20 +553,23 @@ static int step_launch(orl_env* e, const float* actions_dev, float* obs_dev, flo
   // leading blocks that prepare next episodes (they get the lowest block indices: scheduled first when the grid needs several waves)
   d.prep_blocks = d.next_ep ? std::min(16, std::max(1, (e->cfg.num_robot + 255) / 256)) : 0;
   if (e->opt) d.ahead = nullptr;                                  // (clip switching moves the clock inside the step)
-  {
-    // Leading blocks that share an SM with worker blocks of the ONLY wave cost more than they save: their code evicts the
-    // substep loop from the instruction cache of that SM and the launch waits for those workers (8192 robots: 0.1351 ->
-    // 0.1375 ms).  Idle SMs (<= 4608 robots: 0.0844 -> 0.0831 ms) or a grid of several waves (16384 robots: 0.2416 ->
-    // 0.2320 ms) are the two cases that gain (profiles/r02_step_kernel.md section 9).
-    const char* force = getenv("ORL_AHEAD");
-    const bool one_full_wave = e->num_sms - blocks < 4 && blocks <= ORL_STEP_MIN_BLOCKS * e->num_sms;
-    if (one_full_wave && !(force && atoi(force) == 2)) d.ahead = nullptr;
-  }
   if (d.ahead) {
-    // reference packets: one quad-pass per robot; when the workers leave SMs idle (4096 robots = 128 of 148), all of them help
-    // (larger batches: one leading block per 40 chunks of 8 robots, so that the rows exist when the first wave leaves its loop)
+    // Reference packet rows of the next launch: one quad-pass per robot (~13 k cycles per chunk of 8 robots: cold FP64 code),
+    // and the launch lasts until the leading blocks are done.  Two cases gain (profiles/r02_step_kernel.md section 9):
+    //  * the workers leave ENOUGH SMs idle for the rows to take well under a worker's time (one leading block per 28 chunks:
+    //    4096 robots = 128 worker blocks + 20 idle SMs for 512 chunks: 0.0844 -> 0.0831 ms; with 8 blocks the same launch
+    //    takes 0.108 ms, with 4 blocks 0.18 ms: it waits for them) -- all idle SMs help;
+    //  * the grid needs several waves (16384 robots: 0.2416 -> 0.2320 ms): one leading block per 40 chunks.
+    // Leading blocks that share SMs with the worker blocks of the ONLY wave evict the substep loop from those SMs'
+    // instruction caches and the launch waits for those workers (8192 robots: 0.1351 -> 0.1375 ms; sleeping until the first
+    // workers are done did not help either): no rows there, the workers evaluate the reference themselves.
+    const char* force = getenv("ORL_AHEAD");
     const int idle = e->num_sms - blocks, chunks = (e->cfg.num_robot + ORL_ROBOTS_PER_WARP - 1) / ORL_ROBOTS_PER_WARP;
-    d.prep_blocks = idle >= 4 ? std::min(idle, 32) : std::max(d.prep_blocks, std::min(64, std::max(1, chunks / 40)));
+    const int need = (chunks + 27) / 28;
+    if (idle >= need) d.prep_blocks = std::min(idle, std::max(32, need));
+    else if (blocks > ORL_STEP_MIN_BLOCKS * e->num_sms || (force && atoi(force) == 2))
+      d.prep_blocks = std::max(d.prep_blocks, std::min(64, std::max(1, chunks / 40)));
+    else d.ahead = nullptr;
   }
   { static const char* ov = getenv("ORL_PREP_BLOCKS"); if (ov && (d.next_ep || d.ahead)) d.prep_blocks = atoi(ov); }   // experiment knob
   if (d.prep_blocks == 0) { d.next_ep = nullptr; d.prepared = nullptr; d.todo = nullptr; d.ahead = nullptr; }
